@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- filtered Mpixels/s of the single histogram filter on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3] [--dist uniform|blocky]
+
+A "step" is one pass of the filter over one batch of synthetic chunk neighbourhoods. The default workload is C3, the
+configuration BASELINE.json quotes its scaling target on: 256 neighbourhoods (3x3 chunks of 512x512 uint16 biome ids),
+radius 64, 64 biomes; biome ids iid uniform like the reference's own benchmark (STPTestHistogram.cpp:342-343). With N > 1
+(torchrun, one rank per GPU) every rank filters its own 256-chunk batch: independent units, no collective on the data
+path, weak scaling; `value` = pixels of all ranks / max-over-ranks device time.
+
+Printed keys beyond the base contract:
+  roofline      the emitting march kernel: algorithmic bytes of the step / its CUDA-event duration vs the measured HBM peak
+  phases_ms     median CUDA-event time of every kernel phase of a step
+  cpu_baseline  the reference's own filter (oracle/_ref, else the C restatement) timed on this box's host cores on a
+                bounded sample of the same chunks (N=1 only)
+  e2e           same metric through shf_run_batch with HOST buffers: H2D of the inputs and D2H of bins + offsets inside
+                the timed region, sub-batches on two host threads so copies overlap compute
+`--impl reference` times the reference CPU filter alone (all host cores) on the same workload definition.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import dataclasses
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "filtered_mpixels_per_s"
+UNIT = "Mpixels/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "blocky", "rare", "stripes"])
+    ap.add_argument("--chunks", type=int, default=0, help="override the number of chunks per GPU (debugging)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-sub", type=int, default=32, help="chunks per shf_run_batch call in the end-to-end leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_of(args):
+    from superterrainplus_b200 import workloads
+
+    wl = dataclasses.replace(workloads.CONFIGS[args.workload], dist=args.dist)
+    if args.chunks:
+        wl = dataclasses.replace(wl, chunks=args.chunks)
+    return wl
+
+
+def config_of(wl, n_gpus):
+    return {
+        "workload": f"{wl.name}: {wl.chunks} x (3x3 neighbourhood of {wl.map_size[0]}x{wl.map_size[1]} uint16 maps), "
+                    f"radius {wl.radius}, {wl.biomes} biomes, {wl.dist} ids",
+        "chunks_per_gpu": wl.chunks, "map": list(wl.map_size), "radius": wl.radius, "biomes": wl.biomes,
+        "distribution": wl.dist, "sharding": f"chunk batch x{n_gpus}, halos replicated, no collective",
+        "l2": "inputs + outputs per step far exceed the 126 MB L2 (no flush needed)",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own filter (oracle/_ref) or the C restatement. Used by cpu_baseline and --impl reference only.
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_filter_throughput(wl, host_maps, seconds, all_cores):
+    """Mpixels/s of the reference CPU filter over `host_maps` (list of uint16 arrays), bounded by `seconds`."""
+    import oracle
+
+    w, h = wl.map_size
+    cores = os.cpu_count() or 1
+    if oracle.have_reference():
+        kind = "reference"
+        n_workers = max(1, cores // 4) if all_cores else 1  # every filter object owns a fixed 4-thread pool (SHF.cpp:36)
+        sessions = [oracle.ReferenceSession(0xFF) for _ in range(n_workers)]
+        threads_used = 4 * n_workers
+
+        def run(sess, m):
+            sess.run_raw(m, wl.map_size, wl.nn, wl.total, wl.radius)
+    else:
+        kind = "port"
+        n_workers = cores if all_cores else 1
+        sessions = [None] * n_workers
+        threads_used = n_workers
+
+        def run(sess, m):
+            oracle.run_port(m, wl.map_size, wl.nn, wl.radius)
+
+    for s in sessions:  # warm-up: the reference buffer is an adaptive pool (SHF.h:33-34)
+        run(s, host_maps[0])
+    done = [0] * n_workers
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+
+    def worker(i):
+        k = i
+        while time.perf_counter() < deadline:
+            run(sessions[i], host_maps[k % len(host_maps)])
+            done[i] += 1
+            k += n_workers
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(n_workers)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    chunks = sum(done)
+    for s in sessions:
+        if s is not None:
+            s.close()
+    return {"seconds": dt, "value": chunks * w * h / dt / 1e6, "unit": UNIT, "cores": threads_used, "kind": kind,
+            "sample": f"{chunks} chunk calls over {len(host_maps)} distinct chunks of the workload in {dt:.1f} s, "
+                      f"{n_workers} filter object(s) x 4 pool threads, host has {cores} logical cores"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from superterrainplus_b200 import workloads
+
+    wl = workload_of(args)
+    n_distinct = 4
+    host_maps = [workloads.make_map_np(wl, i) for i in range(n_distinct)]
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals, secs = [], []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_filter_throughput(wl, host_maps, per_step, all_cores=True)
+        if i >= args.warmup:
+            vals.append(last["value"])
+            secs.append(last["seconds"])
+    value = statistics.mean(vals)
+    per_step = statistics.mean(secs)
+    w, h = wl.map_size
+    last["value"] = value
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic", "impl": "reference",
+        "config": config_of(wl, args.gpus), "cpu_baseline": last,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import superterrainplus_b200 as pkg
+    from superterrainplus_b200 import api, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the filter has no CPU path (use --impl reference for the CPU filter)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = workload_of(args)
+    w, h = wl.map_size
+    tw, th = wl.total
+    n = wl.chunks
+    info = pkg.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total)
+    maps = workloads.make_maps_torch(wl, rank * n, n, torch.device("cuda", local))
+    torch.cuda.synchronize()
+
+    filt = pkg.STPSingleHistogramFilter(local)
+    FB = pkg.STPSingleHistogramFilter.STPFilterBuffer
+    buf = FB(FB.STPExecutionType.Parallel)
+    stream = torch.cuda.current_stream().cuda_stream
+    api.set_profiling(True)
+
+    def step():
+        filt.runDevice(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    n_bins, _ = buf.size()
+    plan = buf.lastPlan()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    phases = []
+    api.stats_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        phases.append(buf.phaseMs())
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches, _, _ = api.stats()
+    api.set_profiling(False)
+    value = world * n * w * h / (ms_step * 1e-3) / 1e6
+
+    phases_ms = {k: statistics.median(p[k] for p in phases) for k in phases[0]}
+    alg_bytes = workloads.algorithmic_bytes(wl, n_bins)
+    peak, peak_src = measured_peak()
+    emit_ms = phases_ms["march_emit"]
+    achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "march_kernel<K,emit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
+                "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: host buffers in, page-locked host histograms out ----
+    e2e = None
+    if not args.no_e2e:
+        sub = max(1, min(args.e2e_sub, n))
+        host = torch.empty((n, th, tw), dtype=torch.uint16).pin_memory()
+        host.copy_(maps)
+        torch.cuda.synchronize()
+        base_ptr = host.data_ptr()
+        lib = api.library()
+        U2 = ctypes.c_uint32 * 2
+        groups = [(i, min(sub, n - i)) for i in range(0, n, sub)]
+        n_threads = 2 if len(groups) > 1 else 1
+        bufs = [FB(FB.STPExecutionType.Parallel) for _ in range(n_threads)]
+        moved = [[0, 0, 0] for _ in range(n_threads)]
+        errors = []
+
+        def worker(t):
+            try:
+                api.stats_reset()
+                for gi in range(t, len(groups), n_threads):
+                    first, cnt = groups[gi]
+                    ptrs = (ctypes.c_void_p * cnt)(*[base_ptr + (first + j) * th * tw * 2 for j in range(cnt)])
+                    st = lib.shf_run_batch(filt._h, ptrs, cnt, U2(*wl.map_size), U2(*wl.nn), U2(*wl.total), bufs[t]._h,
+                                           wl.radius)
+                    if st != 0:
+                        raise RuntimeError(lib.shf_last_error().decode())
+                    hist = bufs[t].readHistogram()  # the step's result, read on the host
+                    if int(hist.HistogramStartOffset[w * h]) <= 0:
+                        raise RuntimeError("empty result")
+                a, b_, c = api.stats()
+                moved[t] = [a, b_, c]
+            except Exception as exc:  # noqa: BLE001
+                errors.append(exc)
+
+        def e2e_step():
+            ts = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errors:
+                raise errors[0]
+
+        e2e_step()  # warm-up: grows the page-locked buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt / args.e2e_steps)
+        e2e = {"value": world * n * w * h / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": sum(m[1] for m in moved), "d2h_bytes_per_step": sum(m[2] for m in moved),
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "how": f"shf_run_batch on pinned host maps, {sub} chunks per call, {n_threads} host threads with one "
+                      "filter buffer each; bins + offsets copied to page-locked host memory inside the timed region",
+               "gpu_launches_per_step": sum(m[0] for m in moved)}
+        for b_ in bufs:
+            b_.close()
+        del host
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        host_maps = [maps[i].cpu().numpy() for i in range(min(4, n))]
+        cpu = cpu_filter_throughput(wl, host_maps, args.cpu_seconds, all_cores=False)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic",
+            "config": {**config_of(wl, world), "plan": plan, "bins_per_pixel": n_bins / (n * w * h)},
+            "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "impl": "ours",
+        }
+        print(json.dumps(line))
+    buf.close()
+    filt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/*
+ * shf_b200.h -- C ABI of the B200-native single histogram filter.
+ *
+ * This is the drop-in boundary: every entry point below is what a binding of SuperTerrain+'s
+ * `SuperTerrainPlus::STPAlgorithm::STPSingleHistogramFilter` would call. The reference interface each one replaces is
+ * cited as SHF.h / SHF.cpp / SH.hpp:
+ *   SHF.h   = SuperTerrain+/SuperAlgorithm+/Host/Public/SuperAlgorithm+Host/STPSingleHistogramFilter.h
+ *   SHF.cpp = SuperTerrain+/SuperAlgorithm+/Host/Private/STPSingleHistogramFilter.cpp
+ *   SH.hpp  = SuperTerrain+/SuperAlgorithm+/Host/Public/SuperAlgorithm+Host/STPSingleHistogram.hpp
+ * The C++ class with the reference's own names that sits on top of this ABI is in
+ * include/SuperAlgorithm+Host/STPSingleHistogramFilter.h; INTEGRATION.md shows how a maintainer swaps it in.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary. All functions are thread-safe as long as
+ * one shf_buffer is used by one call at a time (the reference's rule, SHF.h:33-34 and
+ * SuperDemo+/World/Biomes/STPBiomefieldGenerator.cpp:102-124). There is no CPU fallback: without a CUDA device every
+ * compute entry point returns SHF_ERR_CUDA.
+ */
+#ifndef SHF_B200_H
+#define SHF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SHF_API __declspec(dllexport)
+#else
+#define SHF_API __attribute__((visibility("default")))
+#endif
+
+/* Layout-identical to STPSingleHistogram::STPBin (SH.hpp:23-37): {uint16 Item; 2 B padding; float Weight}, 8 bytes.
+ * The padding bytes are written as zero by this implementation (the reference leaves them indeterminate). */
+typedef struct shf_bin {
+    uint16_t item;
+    float weight;
+} shf_bin;
+
+typedef struct shf_filter shf_filter; /* <-> STPSingleHistogramFilter object (SHF.h:36) */
+typedef struct shf_buffer shf_buffer; /* <-> STPSingleHistogramFilter::STPFilterBuffer (SHF.h:43-123) */
+
+/* STPFilterBuffer::STPExecutionType (SHF.h:49-52). Both map to the same GPU path; the value is only echoed back. */
+#define SHF_EXEC_SERIAL 0x00u
+#define SHF_EXEC_PARALLEL 0xFFu
+
+enum shf_status {
+    SHF_OK = 0,
+    SHF_ERR_NUMERIC_DOMAIN = 1,  /* <-> STPNumericDomainError, SHF.cpp:874,879-880 */
+    SHF_ERR_INVALID_ENUM = 2,    /* <-> STPInvalidEnum, SHF.cpp:721 */
+    SHF_ERR_CUDA = 3,            /* <-> STPCUDAError (STP_CHECK_CUDA) */
+    SHF_ERR_OFFSET_OVERFLOW = 4, /* total bins of one chunk do not fit HistogramStartOffset's uint32 (SH.hpp:48) */
+    SHF_ERR_UNSUPPORTED = 5,     /* shape outside what the kernels implement; message says which limit */
+    SHF_ERR_INVALID_ARGUMENT = 6
+};
+
+/* ---- filter object: constructor / destructor of STPSingleHistogramFilter (SHF.h:160-170). `device` < 0 = the
+ * calling thread's current CUDA device. The object holds no per-call state and may be shared by threads. */
+SHF_API int shf_filter_create(shf_filter** out, int device);
+SHF_API void shf_filter_destroy(shf_filter* filter);
+
+/* ---- filter buffer: STPFilterBuffer(STPExecutionType) / ~STPFilterBuffer (SHF.h:96-106). A C handle is moved by
+ * copying the pointer. A fresh buffer reads as {NULL, NULL} with size (0, 0) (SHF.cpp:735-750). */
+SHF_API int shf_buffer_create(shf_buffer** out, unsigned char execution_type);
+SHF_API void shf_buffer_destroy(shf_buffer* buffer);
+/* STPFilterBuffer::readHistogram (SHF.h:108-114): pointers into PAGE-LOCKED HOST memory owned by the buffer, valid
+ * until the buffer is reused or destroyed. */
+SHF_API int shf_buffer_read(const shf_buffer* buffer, const shf_bin** bins, const uint32_t** offsets);
+/* STPFilterBuffer::size (SHF.h:116-120): (number of bins, number of offsets = W*H+1 per chunk). */
+SHF_API int shf_buffer_size(const shf_buffer* buffer, size_t* n_bins, size_t* n_offsets);
+/* STPFilterBuffer::type (SHF.h:122-126). */
+SHF_API unsigned char shf_buffer_type(const shf_buffer* buffer);
+
+/* ---- STPSingleHistogramFilter::operator() (SHF.h:172-188, SHF.cpp:870-902).
+ * samplemap: HOST pointer, row-major, row stride total_map_size[0], not retained after return.
+ * map_size / nearest_neighbour / total_map_size: the three uvec2 of STPNearestNeighbourInformation.
+ * Synchronous: on SHF_OK the histogram is complete in the buffer's page-locked host memory. */
+SHF_API int shf_run(shf_filter* filter, const uint16_t* samplemap, const uint32_t map_size[2],
+                    const uint32_t nearest_neighbour[2], const uint32_t total_map_size[2], shf_buffer* buffer,
+                    uint32_t radius);
+
+/* ---- additive entry points (not in the reference) ---- */
+
+/* N independent chunk neighbourhoods of identical geometry in one call. samplemaps[i] is a HOST pointer like shf_run's.
+ * Result in page-locked host memory: bins of all chunks concatenated; offsets as n_chunks blocks of (W*H+1) uint32,
+ * each block relative to its own chunk's first bin; shf_buffer_chunk_base() gives every chunk's first-bin index. */
+SHF_API int shf_run_batch(shf_filter* filter, const uint16_t* const* samplemaps, uint32_t n_chunks,
+                          const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
+                          const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius);
+
+/* Device-resident variant: samplemaps_dev points at n_chunks merged maps in DEVICE memory, chunk i starting at
+ * samplemaps_dev + i * chunk_stride (in samples). The result stays in device memory (shf_buffer_read_device); nothing is
+ * copied to the host except per-chunk bin totals. `stream` is a cudaStream_t (NULL = the legacy default stream); the
+ * call returns after the last kernel has been enqueued on it. */
+SHF_API int shf_run_device(shf_filter* filter, const uint16_t* samplemaps_dev, uint64_t chunk_stride, uint32_t n_chunks,
+                           const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
+                           const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius, void* stream);
+
+/* Device pointers of the last result (bins concatenated, offsets n_chunks x (W*H+1)). */
+SHF_API int shf_buffer_read_device(const shf_buffer* buffer, const shf_bin** bins_dev, const uint32_t** offsets_dev);
+/* Host array of n_chunks+1 first-bin indices (last = total bins) of the last result. */
+SHF_API int shf_buffer_chunk_base(const shf_buffer* buffer, const uint64_t** chunk_base, uint32_t* n_chunks);
+
+/* Message of the last failure on the calling thread: "<expression>: <description>" in the spirit of
+ * STPException::STPBasic::what(), so that the C++ shim can throw the matching exception type. */
+SHF_API const char* shf_last_error(void);
+
+/* Counters for the benchmark harness: kernels launched / bytes copied by this library on the calling thread since the
+ * last reset. */
+SHF_API void shf_stats_reset(void);
+SHF_API void shf_stats_get(uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Kernel configuration chosen by the last call on this buffer (for reports): K = 32-biome register sets per row,
+ * rows per CTA, distinct biomes found, shared memory per CTA. */
+SHF_API int shf_buffer_last_plan(const shf_buffer* buffer, uint32_t* k_sets, uint32_t* rows_per_cta,
+                                 uint32_t* n_biomes, uint32_t* smem_bytes);
+
+/* Measurement hook: when enabled, every call records CUDA events on its stream between the kernel phases
+ * (0 dictionary, 1 remap + vertical scan, 2 counting march, 3 row scan, 4 host round trip for the bin totals,
+ * 5 emitting march); shf_buffer_phase_ms waits for
+ * the last call on the buffer and returns the milliseconds of the first n phases. */
+SHF_API void shf_set_profiling(int enabled);
+SHF_API int shf_buffer_phase_ms(const shf_buffer* buffer, float* ms, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHF_B200_H */

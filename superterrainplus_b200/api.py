@@ -1,0 +1,281 @@
+"""ctypes host layer over include/shf_b200.h with the reference's class and method names.
+
+Reference interface mirrored here (all under SuperTerrain+/):
+  SuperAlgorithm+/Host/Public/SuperAlgorithm+Host/STPSingleHistogramFilter.h:36-192  (filter, filter buffer, operator())
+  SuperAlgorithm+/Host/Public/SuperAlgorithm+Host/STPSingleHistogram.hpp:15-50        (output view)
+  SuperTerrain+/Public/SuperTerrain+/World/Chunk/STPNearestNeighbourInformation.hpp:13-25
+  SuperTerrain+/Public/SuperTerrain+/Exception/STPNumericDomainError.h, STPInvalidEnum.h; Utility/STPDeviceErrorHandler.hpp
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libshf_b200.so"
+
+# STPSingleHistogram::STPBin: {uint16 Item; float Weight}, 8 bytes with 2 bytes of padding after Item
+BIN_DTYPE = np.dtype({"names": ["Item", "Weight"], "formats": ["<u2", "<f4"], "offsets": [0, 4], "itemsize": 8})
+
+SHF_OK, SHF_ERR_NUMERIC_DOMAIN, SHF_ERR_INVALID_ENUM, SHF_ERR_CUDA = 0, 1, 2, 3
+SHF_ERR_OFFSET_OVERFLOW, SHF_ERR_UNSUPPORTED, SHF_ERR_INVALID_ARGUMENT = 4, 5, 6
+
+# every symbol include/shf_b200.h declares (tests check the library exports exactly these)
+C_ABI_SYMBOLS = (
+    "shf_filter_create", "shf_filter_destroy", "shf_buffer_create", "shf_buffer_destroy", "shf_buffer_read",
+    "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_buffer_read_device",
+    "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
+    "shf_set_profiling", "shf_buffer_phase_ms",
+)
+PHASES = ("dictionary", "remap_vscan", "march_count", "rowscan", "host_gap", "march_emit")
+
+
+class STPBasic(Exception):
+    """Base of the exceptions this path can raise (STPException::STPFundamentalException::STPBasic)."""
+
+
+class STPNumericDomainError(STPBasic):
+    """Radius not a positive even number, or wider than the neighbour ring (SHF.cpp:874,879-880)."""
+
+
+class STPInvalidEnum(STPBasic):
+    """Execution type is not a STPFilterBuffer::STPExecutionType (SHF.cpp:721)."""
+
+
+class STPCUDAError(STPBasic):
+    """A CUDA call failed, or there is no device (STP_CHECK_CUDA)."""
+
+
+class STPUnsupportedError(STPBasic):
+    """Shape outside what the kernels implement, or more than 2^32 bins in a chunk."""
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+_lib = None
+_U32x2 = ctypes.c_uint32 * 2
+
+
+def library() -> ctypes.CDLL:
+    """The CUDA library. Fails loudly when it has not been built: there is no other implementation to fall back on."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise STPCUDAError(f"{path} is missing: build it with `python -m superterrainplus_b200.build` "
+                           "(or __graft_entry__.build()); this package has no CPU implementation")
+    lib = ctypes.CDLL(path)
+    vp, u32, u64, sz = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
+    P = ctypes.POINTER
+    lib.shf_filter_create.argtypes = [P(vp), ctypes.c_int]
+    lib.shf_filter_destroy.argtypes = [vp]
+    lib.shf_filter_destroy.restype = None
+    lib.shf_buffer_create.argtypes = [P(vp), ctypes.c_ubyte]
+    lib.shf_buffer_destroy.argtypes = [vp]
+    lib.shf_buffer_destroy.restype = None
+    lib.shf_buffer_read.argtypes = [vp, P(vp), P(vp)]
+    lib.shf_buffer_size.argtypes = [vp, P(sz), P(sz)]
+    lib.shf_buffer_type.argtypes = [vp]
+    lib.shf_buffer_type.restype = ctypes.c_ubyte
+    lib.shf_run.argtypes = [vp, vp, _U32x2, _U32x2, _U32x2, vp, u32]
+    lib.shf_run_batch.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, _U32x2, vp, u32]
+    lib.shf_run_device.argtypes = [vp, vp, u64, u32, _U32x2, _U32x2, _U32x2, vp, u32, vp]
+    lib.shf_buffer_read_device.argtypes = [vp, P(vp), P(vp)]
+    lib.shf_buffer_chunk_base.argtypes = [vp, P(vp), P(u32)]
+    lib.shf_last_error.restype = ctypes.c_char_p
+    lib.shf_stats_reset.restype = None
+    lib.shf_stats_get.argtypes = [P(u64), P(u64), P(u64)]
+    lib.shf_stats_get.restype = None
+    lib.shf_buffer_last_plan.argtypes = [vp, P(u32), P(u32), P(u32), P(u32)]
+    lib.shf_set_profiling.argtypes = [ctypes.c_int]
+    lib.shf_set_profiling.restype = None
+    lib.shf_buffer_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
+    _lib = lib
+    return lib
+
+
+def _raise(status: int) -> None:
+    msg = (library().shf_last_error() or b"").decode("utf-8", "replace")
+    if status == SHF_ERR_NUMERIC_DOMAIN:
+        raise STPNumericDomainError(msg)
+    if status == SHF_ERR_INVALID_ENUM:
+        raise STPInvalidEnum(msg)
+    if status == SHF_ERR_CUDA:
+        raise STPCUDAError(msg)
+    if status in (SHF_ERR_UNSUPPORTED, SHF_ERR_OFFSET_OVERFLOW):
+        raise STPUnsupportedError(msg)
+    raise ValueError(msg)
+
+
+def _check(status: int) -> None:
+    if status != SHF_OK:
+        _raise(status)
+
+
+@dataclass(frozen=True)
+class STPNearestNeighbourInformation:
+    """MapSize, ChunkNearestNeighbour, TotalMapSize as (x, y) pairs (STPNearestNeighbourInformation.hpp:13-25)."""
+
+    MapSize: Tuple[int, int]
+    ChunkNearestNeighbour: Tuple[int, int]
+    TotalMapSize: Tuple[int, int]
+
+
+@dataclass(frozen=True)
+class STPSingleHistogram:
+    """Non-owning view of a filter result (STPSingleHistogram.hpp:15-50): `Bin` is a structured array with fields
+    Item / Weight, `HistogramStartOffset` has W*H+1 entries per chunk. Both alias the filter buffer's page-locked
+    memory and are valid until the buffer is reused or destroyed. A fresh buffer reads as (None, None)."""
+
+    Bin: Optional[np.ndarray]
+    HistogramStartOffset: Optional[np.ndarray]
+
+
+def set_profiling(enabled: bool) -> None:
+    library().shf_set_profiling(1 if enabled else 0)
+
+
+def stats_reset() -> None:
+    library().shf_stats_reset()
+
+
+def stats() -> Tuple[int, int, int]:
+    """(kernel launches, host->device bytes, device->host bytes) issued by this thread since the last reset."""
+    a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    library().shf_stats_get(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
+
+
+class STPSingleHistogramFilter:
+    """GPU single histogram filter with the reference's call signature (SHF.h:160-188)."""
+
+    class STPFilterBuffer:
+        """Opaque scratch + output memory of one filter execution at a time (SHF.h:43-123). Reuse it across calls."""
+
+        class STPExecutionType(enum.IntEnum):
+            Serial = 0x00
+            Parallel = 0xFF
+
+        def __init__(self, execution_type):
+            self._h = ctypes.c_void_p()
+            self._keep = None
+            _check(library().shf_buffer_create(ctypes.byref(self._h), int(execution_type) & 0xFF))
+
+        def close(self) -> None:
+            if getattr(self, "_h", None):
+                library().shf_buffer_destroy(self._h)
+                self._h = ctypes.c_void_p()
+
+        def __del__(self):
+            try:
+                self.close()
+            except Exception:
+                pass
+
+        def readHistogram(self) -> STPSingleHistogram:
+            bins_p, offs_p = ctypes.c_void_p(), ctypes.c_void_p()
+            _check(library().shf_buffer_read(self._h, ctypes.byref(bins_p), ctypes.byref(offs_p)))
+            n_bins, n_offs = self.size()
+            if not offs_p.value:
+                return STPSingleHistogram(None, None)
+            offs = np.ctypeslib.as_array(ctypes.cast(offs_p, ctypes.POINTER(ctypes.c_uint32)), (n_offs,))
+            if n_bins:
+                raw = (ctypes.c_char * (n_bins * BIN_DTYPE.itemsize)).from_address(bins_p.value)
+                bins = np.frombuffer(raw, dtype=BIN_DTYPE)
+            else:
+                bins = np.zeros(0, dtype=BIN_DTYPE)
+            return STPSingleHistogram(bins, offs)
+
+        def size(self) -> Tuple[int, int]:
+            a, b = ctypes.c_size_t(), ctypes.c_size_t()
+            _check(library().shf_buffer_size(self._h, ctypes.byref(a), ctypes.byref(b)))
+            return a.value, b.value
+
+        def type(self) -> "STPSingleHistogramFilter.STPFilterBuffer.STPExecutionType":
+            return self.STPExecutionType(library().shf_buffer_type(self._h))
+
+        # ---- additive (device-resident results) ----
+        def readDevice(self) -> Tuple[int, int]:
+            """(device pointer of the bins, device pointer of the offsets) of the last result."""
+            bins_p, offs_p = ctypes.c_void_p(), ctypes.c_void_p()
+            _check(library().shf_buffer_read_device(self._h, ctypes.byref(bins_p), ctypes.byref(offs_p)))
+            return bins_p.value or 0, offs_p.value or 0
+
+        def chunkBase(self) -> np.ndarray:
+            """First-bin index of every chunk of the last (batch) result, n_chunks+1 entries."""
+            p, n = ctypes.c_void_p(), ctypes.c_uint32()
+            _check(library().shf_buffer_chunk_base(self._h, ctypes.byref(p), ctypes.byref(n)))
+            if not p.value:
+                return np.zeros(0, dtype=np.uint64)
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), (n.value + 1,)).copy()
+
+        def phaseMs(self) -> dict:
+            """Milliseconds of every kernel phase of the last call (needs set_profiling(True) before the call)."""
+            ms = (ctypes.c_float * len(PHASES))()
+            _check(library().shf_buffer_phase_ms(self._h, ms, len(PHASES)))
+            return dict(zip(PHASES, [float(v) for v in ms]))
+
+        def lastPlan(self) -> dict:
+            k, ty, nb, sm = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+            _check(library().shf_buffer_last_plan(self._h, ctypes.byref(k), ctypes.byref(ty), ctypes.byref(nb),
+                                                  ctypes.byref(sm)))
+            return {"k_sets": k.value, "rows_per_cta": ty.value, "biomes": nb.value, "smem_bytes": sm.value}
+
+    def __init__(self, device: int = -1):
+        self._h = ctypes.c_void_p()
+        _check(library().shf_filter_create(ctypes.byref(self._h), device))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            library().shf_filter_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host_map(samplemap, nn_info: STPNearestNeighbourInformation) -> np.ndarray:
+        m = np.ascontiguousarray(samplemap, dtype=np.uint16)
+        if m.size < nn_info.TotalMapSize[0] * nn_info.TotalMapSize[1]:
+            raise ValueError("sample map smaller than TotalMapSize")
+        return m
+
+    def __call__(self, samplemap, nn_info: STPNearestNeighbourInformation, filter_buffer: "STPFilterBuffer",
+                 radius: int) -> STPSingleHistogram:
+        """operator()(samplemap, nn_info, filter_buffer, radius): host map in, page-locked host histogram out."""
+        m = self._host_map(samplemap, nn_info)
+        _check(library().shf_run(self._h, m.ctypes.data, _U32x2(*nn_info.MapSize),
+                                 _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
+                                 filter_buffer._h, radius))
+        return filter_buffer.readHistogram()
+
+    def runBatch(self, samplemaps: Sequence, nn_info: STPNearestNeighbourInformation,
+                 filter_buffer: "STPFilterBuffer", radius: int) -> STPSingleHistogram:
+        """N independent neighbourhoods of equal geometry in one call (additive; shf_run_batch)."""
+        maps = [self._host_map(m, nn_info) for m in samplemaps]
+        arr = (ctypes.c_void_p * len(maps))(*[m.ctypes.data for m in maps])
+        _check(library().shf_run_batch(self._h, arr, len(maps), _U32x2(*nn_info.MapSize),
+                                       _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
+                                       filter_buffer._h, radius))
+        return filter_buffer.readHistogram()
+
+    def runDevice(self, device_ptr: int, chunk_stride: int, n_chunks: int, nn_info: STPNearestNeighbourInformation,
+                  filter_buffer: "STPFilterBuffer", radius: int, stream: int = 0) -> None:
+        """Device-resident variant (additive; shf_run_device): merged maps already in HBM, result stays in HBM."""
+        _check(library().shf_run_device(self._h, device_ptr, chunk_stride, n_chunks, _U32x2(*nn_info.MapSize),
+                                        _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
+                                        filter_buffer._h, radius, stream))
+
+
+STPFilterBuffer = STPSingleHistogramFilter.STPFilterBuffer

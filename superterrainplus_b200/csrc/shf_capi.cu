@@ -1,0 +1,518 @@
+// shf_capi.cu -- the C ABI declared in include/shf_b200.h: handles, growable device / page-locked buffers and the launch
+// sequence of the kernels in shf_kernels.cuh. No torch, no CPU compute path: every result comes from the kernels.
+#include "../../include/shf_b200.h"
+#include "shf_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string tls_error;
+thread_local uint64_t tls_launches = 0, tls_h2d = 0, tls_d2h = 0;
+volatile int g_profiling = 0;  // shf_set_profiling: record CUDA events between the kernel phases
+constexpr int kPhases = 6;     // dictionary | remap + vscan | counting march | row scan | host gap | emitting march
+
+int fail(int status, const char* expr, const std::string& what) {
+    tls_error = std::string(expr) + ": " + what;
+    return status;
+}
+
+#define SHF_CUDA(call)                                                                              \
+    do {                                                                                            \
+        const cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(SHF_ERR_CUDA, #call, std::string(cudaGetErrorString(e_))); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = std::max(bytes, std::min(cap * 2, cap + (size_t(1) << 30)));
+        want = (want + 511) & ~size_t(511);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && want != bytes) {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        cap = (e == cudaSuccess) ? want : 0;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// page-locked host memory: the reference keeps its output in cudaMallocHost memory as well
+// (STPSmartDeviceMemory::makeHost, SHF.cpp:80,105) so that callers can cudaMemcpyAsync from it
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = std::max(bytes, std::min(cap * 2, cap + (size_t(1) << 30)));
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess && want != bytes) {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        }
+        cap = (e == cudaSuccess) ? want : 0;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct shf_filter {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+struct shf_buffer {
+    unsigned char exec_type = SHF_EXEC_PARALLEL;
+    int device = -1;
+    cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
+    DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, basemask, rowtotal, rowbase, chunktotal, chunkbase,
+        bins, hso;
+    PinBuf h_small, h_bins, h_hso;
+    std::vector<uint64_t> chunk_base;  // n_chunks + 1
+    uint32_t n_chunks = 0;
+    size_t n_bins = 0, n_offsets = 0;
+    bool has_result = false, on_host = false;
+    uint32_t plan_k = 0, plan_ty = 0, plan_biomes = 0, plan_smem = 0;
+    cudaEvent_t ev[kPhases + 1] = {};
+    bool ev_valid = false;
+    cudaError_t mark(int i, cudaStream_t s) {
+        if (!g_profiling) return cudaSuccess;
+        if (!ev[i]) {
+            const cudaError_t e = cudaEventCreate(&ev[i]);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaEventRecord(ev[i], s);
+    }
+    void release_all() {
+        for (cudaEvent_t& e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        ev_valid = false;
+        DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
+                       &basemask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso};
+        for (DevBuf* b : d) b->release();
+        h_small.release();
+        h_bins.release();
+        h_hso.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+namespace {
+
+using shf::Geo;
+
+template <int K>
+int launch_chain(const shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_view, cudaStream_t s, bool emit) {
+    const size_t smem = (size_t)g.TY * g.R * g.VS + (size_t)g.TY * 2 * 32 * K * 4 + 32 * K * 2;
+    if (!emit) {
+        const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
+        const size_t vsmem = (size_t)shf::kVscanThreads * (5 * 32 * K + 4);
+        SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+        shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(),
+                                                                     b->base.as<uint8_t>(), b->basemask.as<uint32_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+        SHF_CUDA(b->mark(2, s));
+        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::march_kernel<K, false><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->basemask.as<uint32_t>(),
+            b->dict.as<uint16_t>(), 32 * K, b->rowtotal.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    } else {
+        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::march_kernel<K, true><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->basemask.as<uint32_t>(),
+            b->dict.as<uint16_t>(), 32 * K, nullptr, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(),
+            b->bins.as<uint2>(), b->hso.as<uint32_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    }
+    (void)f;
+    (void)in_view;
+    return SHF_OK;
+}
+
+int dispatch_chain(int K, const shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_view, cudaStream_t s,
+                   bool emit) {
+    switch (K) {
+        case 1: return launch_chain<1>(f, b, g, in_view, s, emit);
+        case 2: return launch_chain<2>(f, b, g, in_view, s, emit);
+        case 4: return launch_chain<4>(f, b, g, in_view, s, emit);
+        case 8: return launch_chain<8>(f, b, g, in_view, s, emit);
+    }
+    return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
+}
+
+// SHF.cpp:874-880
+int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) {
+    if (!(radius > 0u && (radius & 1u) == 0u))
+        return fail(SHF_ERR_NUMERIC_DOMAIN, "radius > 0u && (radius & 0x01u) == 0x00u",
+                    "The radius of the filter kernel must be a positive even number");
+    const uint64_t sx = (uint64_t)map_size[0] * (nn[0] / 2u), sy = (uint64_t)map_size[1] * (nn[1] / 2u);
+    if (radius > sx || radius > sy)
+        return fail(SHF_ERR_NUMERIC_DOMAIN, "radius <= start_coord",
+                    "The radius of the filter kernel is too large and will overflow the free-slip boundary");
+    return SHF_OK;
+}
+
+// Run the whole kernel sequence. `in_dev` views the halo-extended region of every chunk in device memory.
+int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t in_chunk_stride, uint32_t in_row_stride,
+                  uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s) {
+    Geo g{};
+    g.W = W;
+    g.H = H;
+    g.r = r;
+    g.span = 2u * r + 1u;
+    g.PW = W + 2u * r;
+    g.PH = H + 2u * r;
+    g.P = (g.PW + 7u) & ~7u;
+    g.n_chunks = n_chunks;
+    g.in_row_stride = in_row_stride;
+    g.in_chunk_stride = in_chunk_stride;
+    g.inv_total = 1.0f / (float)(g.span * g.span);
+    if (W == 0u || H == 0u || n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "W*H*n_chunks > 0", "empty input");
+    if (n_chunks > 65535u) return fail(SHF_ERR_UNSUPPORTED, "n_chunks <= 65535", "too many chunks in one batch");
+    if (g.span > 255u)
+        return fail(SHF_ERR_UNSUPPORTED, "2*radius+1 <= 255", "radius above 126 needs 16-bit window counters (not built yet)");
+    if (g.PH >= 65535u) return fail(SHF_ERR_UNSUPPORTED, "H + 2*radius < 65535", "map too tall for 16-bit row keys");
+
+    const size_t cells = (size_t)n_chunks * g.PH * g.P;
+    SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
+    SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
+    SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
+    SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 16));
+    uint32_t* h_nbiomes = b->h_small.as<uint32_t>();
+    uint64_t* h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
+
+    // ---- dictionary ----
+    b->ev_valid = false;
+    SHF_CUDA(b->mark(0, s));
+    SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
+    const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), n_chunks);
+    shf::presence_kernel<<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
+    tls_launches++;
+    shf::dict_prefix_kernel<<<n_chunks, 256, 0, s>>>(b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                     b->nbiomes.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    SHF_CUDA(b->mark(1, s));
+    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
+    tls_d2h += (size_t)n_chunks * 4;
+    SHF_CUDA(cudaStreamSynchronize(s));
+    uint32_t bmax = 0;
+    for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
+    if (bmax > 256u)
+        return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 256",
+                    "more than 256 distinct biomes in one neighbourhood (wide-list kernel not built yet)");
+    const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
+    g.K = K;
+    g.Bpad = 32u * K;
+    g.R = g.span + shf::kBatchCols;
+    g.VS = (4u * K + g.Bpad);
+    if (((g.VS / 4u) & 1u) == 0u) g.VS += 4u;
+    // rows per CTA: as many as fit the shared memory, at most 16 (and at most H)
+    uint32_t ty = std::min<uint32_t>(16u, H);
+    auto smem_of = [&](uint32_t t) { return (size_t)t * g.R * g.VS + (size_t)t * 2 * 32 * K * 4 + 32 * K * 2; };
+    while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
+    if (smem_of(ty) > f->smem_optin)
+        return fail(SHF_ERR_UNSUPPORTED, "ring fits shared memory", "radius x biome count too large for one CTA");
+    g.TY = ty;
+    g.T = (H + ty - 1u) / ty;
+    b->plan_k = K;
+    b->plan_ty = ty;
+    b->plan_biomes = bmax;
+    b->plan_smem = (uint32_t)smem_of(ty);
+
+    SHF_CUDA(b->cmap.ensure(cells * 2));
+    SHF_CUDA(b->vstart.ensure(cells * 2));
+    SHF_CUDA(b->dict.ensure((size_t)n_chunks * g.Bpad * 2));
+    SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
+    SHF_CUDA(b->basemask.ensure((size_t)n_chunks * g.T * g.PW * K * 4));
+    SHF_CUDA(b->rowtotal.ensure((size_t)n_chunks * H * 4));
+    SHF_CUDA(b->rowbase.ensure((size_t)n_chunks * H * 4));
+    SHF_CUDA(b->chunktotal.ensure((size_t)n_chunks * 8));
+    SHF_CUDA(b->chunkbase.ensure((size_t)(n_chunks + 1) * 8));
+    const size_t n_off = (size_t)n_chunks * ((size_t)W * H + 1u);
+    SHF_CUDA(b->hso.ensure(n_off * 4));
+
+    shf::remap_kernel<<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                            b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+
+    // ---- vertical scan + counting march ----
+    int st = dispatch_chain(K, f, b, g, in_dev, s, false);
+    if (st != SHF_OK) return st;
+    SHF_CUDA(b->mark(3, s));
+    shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+                                                  b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    SHF_CUDA(b->mark(4, s));
+    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
+    tls_d2h += (size_t)n_chunks * 8;
+    SHF_CUDA(cudaStreamSynchronize(s));
+    b->chunk_base.assign(n_chunks + 1u, 0ull);
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        if (h_totals[i] > 0xFFFFFFFFull)
+            return fail(SHF_ERR_OFFSET_OVERFLOW, "bins per chunk < 2^32",
+                        "HistogramStartOffset is 32 bits wide; this chunk has too many bins");
+        b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
+    }
+    const size_t total = (size_t)b->chunk_base[n_chunks];
+    SHF_CUDA(b->bins.ensure(std::max<size_t>(total, 1) * sizeof(shf_bin)));
+    SHF_CUDA(cudaMemcpyAsync(b->chunkbase.p, b->chunk_base.data(), (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
+    tls_h2d += (size_t)(n_chunks + 1) * 8;
+
+    // ---- emitting march ----
+    SHF_CUDA(b->mark(5, s));
+    st = dispatch_chain(K, f, b, g, in_dev, s, true);
+    if (st != SHF_OK) return st;
+    SHF_CUDA(b->mark(6, s));
+    b->ev_valid = g_profiling != 0;
+    b->n_chunks = n_chunks;
+    b->n_bins = total;
+    b->n_offsets = n_off;
+    b->has_result = true;
+    b->on_host = false;
+    return SHF_OK;
+}
+
+int bind_device(const shf_filter* f, shf_buffer* b) {
+    SHF_CUDA(cudaSetDevice(f->device));
+    if (b->device != f->device) {
+        if (b->device >= 0) {
+            cudaSetDevice(b->device);
+            b->release_all();
+            cudaSetDevice(f->device);
+        }
+        b->device = f->device;
+    }
+    if (!b->stream) SHF_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    return SHF_OK;
+}
+
+int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, const uint32_t map_size[2],
+             const uint32_t nn[2], const uint32_t total[2], shf_buffer* b, uint32_t radius) {
+    if (!f || !b || !maps || !map_size || !nn || !total)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    int st = validate(map_size, nn, radius);
+    if (st != SHF_OK) return st;
+    st = bind_device(f, b);
+    if (st != SHF_OK) return st;
+    const uint32_t W = map_size[0], H = map_size[1], r = radius;
+    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 7u) & ~7u;
+    const size_t sx = (size_t)W * (nn[0] / 2u), sy = (size_t)H * (nn[1] / 2u);
+    const size_t S = total[0];
+    if (S < sx + W + r) return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.x >= start + W + r", "row stride too small");
+    b->has_result = false;
+    cudaStream_t s = b->stream;
+    const size_t cells = (size_t)PH * P;
+    SHF_CUDA(b->din.ensure((size_t)n_chunks * cells * 2));
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        if (!maps[i]) return fail(SHF_ERR_INVALID_ARGUMENT, "samplemap != NULL", "null sample map");
+        const uint16_t* src = maps[i] + (sy - r) * S + (sx - r);
+        SHF_CUDA(cudaMemcpy2DAsync(b->din.as<uint16_t>() + (size_t)i * cells, (size_t)P * 2, src, S * 2, (size_t)PW * 2, PH,
+                                   cudaMemcpyHostToDevice, s));
+        tls_h2d += (size_t)PW * 2 * PH;
+    }
+    st = run_on_device(f, b, b->din.as<uint16_t>(), cells, P, n_chunks, W, H, r, s);
+    if (st != SHF_OK) return st;
+    // result to page-locked host memory
+    SHF_CUDA(b->h_bins.ensure(std::max<size_t>(b->n_bins, 1) * sizeof(shf_bin)));
+    SHF_CUDA(b->h_hso.ensure(b->n_offsets * 4));
+    if (b->n_bins) {
+        SHF_CUDA(cudaMemcpyAsync(b->h_bins.p, b->bins.p, b->n_bins * sizeof(shf_bin), cudaMemcpyDeviceToHost, s));
+        tls_d2h += b->n_bins * sizeof(shf_bin);
+    }
+    SHF_CUDA(cudaMemcpyAsync(b->h_hso.p, b->hso.p, b->n_offsets * 4, cudaMemcpyDeviceToHost, s));
+    tls_d2h += b->n_offsets * 4;
+    SHF_CUDA(cudaStreamSynchronize(s));
+    b->on_host = true;
+    return SHF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shf_filter_create(shf_filter** out, int device) {
+    if (!out) return fail(SHF_ERR_INVALID_ARGUMENT, "out != NULL", "null argument");
+    *out = nullptr;
+    int count = 0;
+    SHF_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail(SHF_ERR_CUDA, "cudaGetDeviceCount", "no CUDA device: this filter has no CPU path");
+    if (device < 0) SHF_CUDA(cudaGetDevice(&device));
+    if (device >= count) return fail(SHF_ERR_INVALID_ARGUMENT, "device < device count", "no such device");
+    shf_filter* f = new (std::nothrow) shf_filter();
+    if (!f) return fail(SHF_ERR_INVALID_ARGUMENT, "new shf_filter", "out of host memory");
+    f->device = device;
+    int v = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) {
+        f->sm_count = v;
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    }
+    if (e != cudaSuccess) {
+        delete f;
+        return fail(SHF_ERR_CUDA, "cudaDeviceGetAttribute", cudaGetErrorString(e));
+    }
+    f->smem_optin = (size_t)v;
+    *out = f;
+    return SHF_OK;
+}
+
+void shf_filter_destroy(shf_filter* filter) { delete filter; }
+
+int shf_buffer_create(shf_buffer** out, unsigned char execution_type) {
+    if (!out) return fail(SHF_ERR_INVALID_ARGUMENT, "out != NULL", "null argument");
+    *out = nullptr;
+    if (execution_type != SHF_EXEC_SERIAL && execution_type != SHF_EXEC_PARALLEL)
+        return fail(SHF_ERR_INVALID_ENUM, "STPExecutionType", "value is not a valid STPFilterBuffer::STPExecutionType");
+    shf_buffer* b = new (std::nothrow) shf_buffer();
+    if (!b) return fail(SHF_ERR_INVALID_ARGUMENT, "new shf_buffer", "out of host memory");
+    b->exec_type = execution_type;
+    *out = b;
+    return SHF_OK;
+}
+
+void shf_buffer_destroy(shf_buffer* buffer) {
+    if (!buffer) return;
+    if (buffer->device >= 0) {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(buffer->device);
+        buffer->release_all();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    delete buffer;
+}
+
+int shf_buffer_read(const shf_buffer* b, const shf_bin** bins, const uint32_t** offsets) {
+    if (!b || !bins || !offsets) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (!b->has_result || !b->on_host) {
+        *bins = nullptr;
+        *offsets = nullptr;
+        return SHF_OK;
+    }
+    *bins = b->h_bins.as<shf_bin>();
+    *offsets = b->h_hso.as<uint32_t>();
+    return SHF_OK;
+}
+
+int shf_buffer_size(const shf_buffer* b, size_t* n_bins, size_t* n_offsets) {
+    if (!b || !n_bins || !n_offsets) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    *n_bins = b->has_result ? b->n_bins : 0;
+    *n_offsets = b->has_result ? b->n_offsets : 0;
+    return SHF_OK;
+}
+
+unsigned char shf_buffer_type(const shf_buffer* b) { return b ? b->exec_type : 0; }
+
+int shf_run(shf_filter* filter, const uint16_t* samplemap, const uint32_t map_size[2], const uint32_t nn[2],
+            const uint32_t total[2], shf_buffer* buffer, uint32_t radius) {
+    const uint16_t* maps[1] = {samplemap};
+    return run_host(filter, maps, 1u, map_size, nn, total, buffer, radius);
+}
+
+int shf_run_batch(shf_filter* filter, const uint16_t* const* samplemaps, uint32_t n_chunks, const uint32_t map_size[2],
+                  const uint32_t nn[2], const uint32_t total[2], shf_buffer* buffer, uint32_t radius) {
+    if (n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "n_chunks > 0", "empty batch");
+    return run_host(filter, samplemaps, n_chunks, map_size, nn, total, buffer, radius);
+}
+
+int shf_run_device(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_stride, uint32_t n_chunks,
+                   const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], shf_buffer* b,
+                   uint32_t radius, void* stream) {
+    if (!f || !b || !maps_dev || !map_size || !nn || !total)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    int st = validate(map_size, nn, radius);
+    if (st != SHF_OK) return st;
+    st = bind_device(f, b);
+    if (st != SHF_OK) return st;
+    const uint32_t W = map_size[0], H = map_size[1];
+    const size_t sx = (size_t)W * (nn[0] / 2u), sy = (size_t)H * (nn[1] / 2u);
+    const size_t S = total[0];
+    if (S < sx + W + radius) return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.x >= start + W + r", "row stride too small");
+    b->has_result = false;
+    const uint16_t* view = maps_dev + (sy - radius) * S + (sx - radius);
+    return run_on_device(f, b, view, chunk_stride, (uint32_t)S, n_chunks, W, H, radius, static_cast<cudaStream_t>(stream));
+}
+
+int shf_buffer_read_device(const shf_buffer* b, const shf_bin** bins_dev, const uint32_t** offsets_dev) {
+    if (!b || !bins_dev || !offsets_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    *bins_dev = b->has_result ? b->bins.as<shf_bin>() : nullptr;
+    *offsets_dev = b->has_result ? b->hso.as<uint32_t>() : nullptr;
+    return SHF_OK;
+}
+
+int shf_buffer_chunk_base(const shf_buffer* b, const uint64_t** chunk_base, uint32_t* n_chunks) {
+    if (!b || !chunk_base || !n_chunks) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    *chunk_base = b->has_result ? b->chunk_base.data() : nullptr;
+    *n_chunks = b->has_result ? b->n_chunks : 0u;
+    return SHF_OK;
+}
+
+const char* shf_last_error(void) { return tls_error.c_str(); }
+
+void shf_stats_reset(void) { tls_launches = tls_h2d = tls_d2h = 0; }
+
+void shf_stats_get(uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (kernel_launches) *kernel_launches = tls_launches;
+    if (h2d_bytes) *h2d_bytes = tls_h2d;
+    if (d2h_bytes) *d2h_bytes = tls_d2h;
+}
+
+void shf_set_profiling(int enabled) { g_profiling = enabled ? 1 : 0; }
+
+int shf_buffer_phase_ms(const shf_buffer* b, float* ms, uint32_t n) {
+    if (!b || !ms) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (!b->ev_valid) return fail(SHF_ERR_INVALID_ARGUMENT, "profiling enabled", "no phase events recorded for the last call");
+    SHF_CUDA(cudaEventSynchronize(b->ev[kPhases]));
+    for (uint32_t i = 0; i < n && i < (uint32_t)kPhases; i++) SHF_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    return SHF_OK;
+}
+
+int shf_buffer_last_plan(const shf_buffer* b, uint32_t* k_sets, uint32_t* rows_per_cta, uint32_t* n_biomes,
+                         uint32_t* smem_bytes) {
+    if (!b) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer != NULL", "null argument");
+    if (k_sets) *k_sets = b->plan_k;
+    if (rows_per_cta) *rows_per_cta = b->plan_ty;
+    if (n_biomes) *n_biomes = b->plan_biomes;
+    if (smem_bytes) *smem_bytes = b->plan_smem;
+    return SHF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes host layer), against the CPU oracle on the same inputs.
+
+Bar: items, offsets AND weight bits identical to the reference filter. The oracle used is oracle/shf_oracle.c (pinned
+to the reference's golden vector and to the reference's own compiled filter by tests/test_oracle.py); where the
+reference build travelled to this box (oracle/_ref) it is checked too.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_same, split_result
+
+pytestmark = pytest.mark.gpu
+
+
+def nn_info(shf, w, h, nn=(3, 3)):
+    return shf.STPNearestNeighbourInformation((w, h), nn, (w * nn[0], h * nn[1]))
+
+
+@pytest.fixture(scope="module")
+def filt(shf):
+    return shf.STPSingleHistogramFilter()
+
+
+from golden.reference_vector import EXPECTED, TEXTURE as GOLDEN_TEXTURE, WEIGHT_RTOL, BAD_RADII
+
+
+def random_map(rng, w, h, biomes, kind, nn=(3, 3)):
+    tw, th = w * nn[0], h * nn[1]
+    if kind == "iid":
+        m = rng.integers(0, biomes, (th, tw))
+    elif kind == "blocky":
+        bs = int(rng.integers(2, 9))
+        m = rng.integers(0, biomes, (th // bs + 1, tw // bs + 1)).repeat(bs, 0).repeat(bs, 1)[:th, :tw]
+    elif kind == "rare":
+        m = np.where(rng.random((th, tw)) < 0.95, 0, rng.integers(0, biomes, (th, tw)))
+    elif kind == "stripes":
+        period = int(rng.integers(2, 12))
+        m = np.broadcast_to((np.arange(tw) % period)[None, :] % biomes, (th, tw))
+    elif kind == "hstripes":
+        period = int(rng.integers(2, 12))
+        m = np.broadcast_to((np.arange(th) % period)[:, None] % biomes, (th, tw))
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(m, dtype=np.uint16)
+
+
+def test_golden_all_pixels(shf, filt, oracle_mod):
+    info = nn_info(shf, 4, 4)
+    for exec_type in (shf.STPSingleHistogramFilter.STPFilterBuffer.STPExecutionType.Serial,
+                      shf.STPSingleHistogramFilter.STPFilterBuffer.STPExecutionType.Parallel):
+        buf = shf.STPSingleHistogramFilter.STPFilterBuffer(exec_type)
+        assert buf.size() == (0, 0)
+        assert buf.readHistogram().Bin is None
+        hist = filt(GOLDEN_TEXTURE, info, buf, 2)
+        got = split_result(hist)
+        want = oracle_mod.run_port(GOLDEN_TEXTURE, (4, 4), (3, 3), 2)
+        assert_same(got, want, "golden")
+        # the three pixels the reference test pins (STPTestHistogram.cpp:77-94)
+        for px, bins in EXPECTED.items():
+            lo, hi = int(got[2][px]), int(got[2][px + 1])
+            assert list(got[0][lo:hi]) == [b[0] for b in bins]
+            np.testing.assert_allclose(got[1][lo:hi], [b[1] for b in bins], rtol=WEIGHT_RTOL)
+        # STPTestHistogram.cpp:150-161: same buffer again gives the same result; size and type echo
+        again = split_result(filt(GOLDEN_TEXTURE, info, buf, 2))
+        assert_same(again, want, "golden rerun")
+        assert buf.size() == (64, 17)
+        assert buf.type() == exec_type
+        buf.close()
+
+
+def test_error_cases(shf, filt):
+    info = nn_info(shf, 4, 4)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    for bad in BAD_RADII:  # STPTestHistogram.cpp:125-129
+        with pytest.raises(shf.STPNumericDomainError):
+            filt(GOLDEN_TEXTURE, info, buf, bad)
+    with pytest.raises(shf.STPNumericDomainError):  # 1x1 neighbourhood rejects every radius (SHF.cpp:876-880)
+        filt(GOLDEN_TEXTURE, shf.STPNearestNeighbourInformation((12, 12), (1, 1), (12, 12)), buf, 2)
+    with pytest.raises(shf.STPInvalidEnum):
+        shf.STPSingleHistogramFilter.STPFilterBuffer(0x42)
+
+
+CASES = []
+_rng = np.random.default_rng(20251017)
+for _i in range(48):
+    _w, _h = int(_rng.integers(4, 40)), int(_rng.integers(4, 40))
+    _r = 2 * int(_rng.integers(1, max(2, min(_w, _h) // 2 + 1)))
+    _r = min(_r, min(_w, _h) // 2 * 2)
+    CASES.append((_w, _h, _r, int(_rng.integers(1, 40)), ["iid", "blocky", "rare", "stripes", "hstripes"][_i % 5], _i))
+
+
+@pytest.mark.parametrize("w,h,r,biomes,kind,seed", CASES)
+def test_small_random(shf, filt, oracle_mod, w, h, r, biomes, kind, seed):
+    rng = np.random.default_rng(seed)
+    m = random_map(rng, w, h, biomes, kind)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, nn_info(shf, w, h), buf, r))
+    assert_same(got, oracle_mod.run_port(m, (w, h), (3, 3), r), f"{w}x{h} r={r} B={biomes} {kind}")
+    buf.close()
+
+
+@pytest.mark.parametrize("w,h,r,biomes,kind", [
+    (64, 64, 32, 200, "iid"), (130, 96, 64, 256, "iid"), (48, 160, 48, 5, "blocky"), (96, 80, 16, 64, "blocky"),
+    (128, 128, 64, 64, "iid"), (100, 70, 8, 33, "rare"), (72, 72, 36, 65, "stripes"), (200, 50, 50, 129, "iid"),
+    (64, 200, 126, 16, "blocky"),
+])
+def test_medium(shf, filt, oracle_mod, w, h, r, biomes, kind):
+    rng = np.random.default_rng(w * 1000 + h)
+    nn = (3, 3) if r <= min(w, h) else (2 * ((r + min(w, h) - 1) // min(w, h)) + 1,) * 2
+    m = random_map(rng, w, h, biomes, kind, nn)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+    assert_same(got, oracle_mod.run_port(m, (w, h), nn, r), f"{w}x{h} r={r} B={biomes} {kind}")
+    buf.close()
+
+
+def test_sparse_ids_and_non_square_neighbourhood(shf, filt, oracle_mod):
+    # sample values are arbitrary uint16 (SHF.cpp:404-410 grows its dictionary to max id + 1)
+    rng = np.random.default_rng(5)
+    ids = np.array([0, 7, 300, 4095, 65535, 12345, 32768], dtype=np.uint16)
+    m = ids[rng.integers(0, len(ids), (5 * 20, 3 * 24))]
+    info = shf.STPNearestNeighbourInformation((24, 20), (3, 5), (72, 100))
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0x00)
+    got = split_result(filt(m, info, buf, 10))
+    assert_same(got, oracle_mod.run_port(m, (24, 20), (3, 5), 10), "sparse ids")
+    buf.close()
+
+
+def test_batch_matches_single(shf, filt, oracle_mod):
+    rng = np.random.default_rng(9)
+    w, h, r = 40, 24, 12
+    maps = [random_map(rng, w, h, 20, k) for k in ("iid", "blocky", "rare", "stripes", "iid")]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    hist = filt.runBatch(maps, nn_info(shf, w, h), buf, r)
+    base = buf.chunkBase()
+    assert len(base) == len(maps) + 1 and base[-1] == len(hist.Bin)
+    per = w * h + 1
+    for i, m in enumerate(maps):
+        items = hist.Bin["Item"][base[i]:base[i + 1]].copy()
+        weights = hist.Bin["Weight"][base[i]:base[i + 1]].copy()
+        offs = hist.HistogramStartOffset[i * per:(i + 1) * per].copy()
+        assert_same((items, weights, offs), oracle_mod.run_port(m, (w, h), (3, 3), r), f"batch chunk {i}")
+    buf.close()
+
+
+def test_device_resident(shf, filt, oracle_mod):
+    import torch
+
+    rng = np.random.default_rng(11)
+    w, h, r = 32, 32, 8
+    maps = np.stack([random_map(rng, w, h, 12, k) for k in ("iid", "blocky", "rare")])
+    dev = torch.from_numpy(maps.view(np.int16)).cuda()
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    filt.runDevice(dev.data_ptr(), maps.shape[1] * maps.shape[2], 3, nn_info(shf, w, h), buf, r,
+                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    bins_p, offs_p = buf.readDevice()
+    base = buf.chunkBase()
+    n_bins, n_offs = buf.size()
+    assert n_bins == base[-1] and n_offs == 3 * (w * h + 1)
+    import ctypes
+    cudart = ctypes.CDLL("libcudart.so.12")
+    bins = np.zeros(n_bins, dtype=shf.BIN_DTYPE)
+    offs = np.zeros(n_offs, dtype=np.uint32)
+    assert cudart.cudaMemcpy(ctypes.c_void_p(bins.ctypes.data), ctypes.c_void_p(bins_p), ctypes.c_size_t(bins.nbytes), 2) == 0
+    assert cudart.cudaMemcpy(ctypes.c_void_p(offs.ctypes.data), ctypes.c_void_p(offs_p), ctypes.c_size_t(offs.nbytes), 2) == 0
+    per = w * h + 1
+    for i in range(3):
+        got = (bins["Item"][base[i]:base[i + 1]].copy(), bins["Weight"][base[i]:base[i + 1]].copy(),
+               offs[i * per:(i + 1) * per].copy())
+        assert_same(got, oracle_mod.run_port(maps[i], (w, h), (3, 3), r), f"device chunk {i}")
+    buf.close()
+
+
+@pytest.mark.parametrize("name,dist", [("C1", "uniform"), ("C1", "blocky"), ("C2", "blocky")])
+def test_baseline_configs_vs_oracle(shf, filt, oracle_mod, name, dist):
+    """BASELINE.json configs small enough for the oracle to finish in seconds: full comparison."""
+    import dataclasses
+    from superterrainplus_b200 import workloads
+
+    wl = dataclasses.replace(workloads.CONFIGS[name], dist=dist)
+    m = workloads.make_map_np(wl, 0)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, shf.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total), buf, wl.radius))
+    assert_same(got, oracle_mod.run_port(m, wl.map_size, wl.nn, wl.radius), f"{name} {dist}")
+    buf.close()
+
+
+def test_c3_batch_properties_and_sampled_chunks(shf, filt, oracle_mod):
+    """C3 shape (512x512, r=64, 64 biomes) on a 6-chunk batch: two chunks against the oracle in full, all chunks through
+    size-independent properties (offsets monotone and consistent with the bin total, window counts sum to (2r+1)^2,
+    items distinct within a pixel, every bin non-empty)."""
+    import dataclasses
+    from superterrainplus_b200 import workloads
+
+    wl = dataclasses.replace(workloads.CONFIGS["C3"], chunks=6)
+    maps = [workloads.make_map_np(dataclasses.replace(wl, dist=("uniform" if i % 2 == 0 else "blocky")), i)
+            for i in range(wl.chunks)]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    hist = filt.runBatch(maps, shf.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total), buf, wl.radius)
+    base = buf.chunkBase()
+    w, h = wl.map_size
+    per = w * h + 1
+    total = (2 * wl.radius + 1) ** 2
+    inv = np.float32(1.0) / np.float32(total)
+    for i in range(wl.chunks):
+        offs = hist.HistogramStartOffset[i * per:(i + 1) * per].astype(np.int64)
+        items = hist.Bin["Item"][base[i]:base[i + 1]]
+        weights = hist.Bin["Weight"][base[i]:base[i + 1]]
+        assert offs[0] == 0 and offs[-1] == base[i + 1] - base[i]
+        nb = np.diff(offs)
+        assert (nb >= 1).all() and (nb <= wl.biomes).all()
+        counts = np.rint(weights.astype(np.float64) * total).astype(np.int64)
+        assert (counts >= 1).all()
+        assert np.array_equal((counts.astype(np.float32) * inv).view(np.uint32), weights.view(np.uint32))
+        sums = np.add.reduceat(counts, offs[:-1])
+        assert (sums == total).all()
+        # distinct items per pixel: sort (pixel, item) pairs and look for equal neighbours
+        px = np.repeat(np.arange(w * h, dtype=np.int64), nb)
+        key = np.sort(px * 65536 + items.astype(np.int64))
+        assert (np.diff(key) != 0).all()
+        if i < 2:
+            want = oracle_mod.run_port(maps[i], wl.map_size, wl.nn, wl.radius)
+            assert_same((items.copy(), weights.copy(), offs.astype(np.uint32)), want, f"C3 chunk {i}")
+    buf.close()

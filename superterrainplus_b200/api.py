@@ -32,7 +32,7 @@ C_ABI_SYMBOLS = (
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
     "shf_set_profiling", "shf_buffer_phase_ms",
 )
-PHASES = ("dictionary", "remap_vscan", "march_count", "rowscan", "host_gap", "march_emit")
+PHASES = ("dictionary", "remap_vscan", "rowcount", "rowscan", "host_gap", "march_emit")
 
 
 class STPBasic(Exception):

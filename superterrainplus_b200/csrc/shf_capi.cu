@@ -93,7 +93,7 @@ struct shf_buffer {
     unsigned char exec_type = SHF_EXEC_PARALLEL;
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
-    DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, basemask, rowtotal, rowbase, chunktotal, chunkbase,
+    DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
         bins, hso;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
@@ -118,7 +118,7 @@ struct shf_buffer {
         }
         ev_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
-                       &basemask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso};
+                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -132,45 +132,52 @@ namespace {
 
 using shf::Geo;
 
+size_t march_smem(uint32_t ty, uint32_t R, int K) {
+    return (size_t)ty * R * 32 * K + (size_t)ty * R * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2;
+}
+
+// phase 0: vertical scan + bins per row; phase 1: the emitting march
 template <int K>
-int launch_chain(const shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_view, cudaStream_t s, bool emit) {
-    const size_t smem = (size_t)g.TY * g.R * g.VS + (size_t)g.TY * 2 * 32 * K * 4 + 32 * K * 2;
-    if (!emit) {
+int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
+    if (phase == 0) {
         const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
         const size_t vsmem = (size_t)shf::kVscanThreads * (5 * 32 * K + 4);
         SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
         shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(),
-                                                                     b->base.as<uint8_t>(), b->basemask.as<uint32_t>());
+                                                                     b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));
-        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::march_kernel<K, false><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
-            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->basemask.as<uint32_t>(),
-            b->dict.as<uint16_t>(), 32 * K, b->rowtotal.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+        // one warp per row; shrink the CTA until its two mask rows per warp fit
+        uint32_t warps = 4;
+        const size_t per_warp = (size_t)2 * g.PW * K * 4;
+        while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+        if (per_warp > 200 * 1024) return fail(SHF_ERR_UNSUPPORTED, "row masks fit shared memory", "map too wide");
+        SHF_CUDA(cudaFuncSetAttribute(shf::rowcount_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(warps * per_warp)));
+        shf::rowcount_kernel<K><<<dim3((g.H + warps - 1) / warps, g.n_chunks), warps * 32, warps * per_warp, s>>>(
+            g, b->colmask.as<uint32_t>(), b->rowtotal.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
     } else {
-        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::march_kernel<K, true><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
-            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->basemask.as<uint32_t>(),
-            b->dict.as<uint16_t>(), 32 * K, nullptr, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(),
-            b->bins.as<uint2>(), b->hso.as<uint32_t>());
+        const size_t smem = march_smem(g.TY, g.R, K);
+        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
+            b->dict.as<uint16_t>(), 32 * K, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(),
+            b->hso.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
     }
-    (void)f;
-    (void)in_view;
     return SHF_OK;
 }
 
-int dispatch_chain(int K, const shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_view, cudaStream_t s,
-                   bool emit) {
+int dispatch_chain(int K, shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     switch (K) {
-        case 1: return launch_chain<1>(f, b, g, in_view, s, emit);
-        case 2: return launch_chain<2>(f, b, g, in_view, s, emit);
-        case 4: return launch_chain<4>(f, b, g, in_view, s, emit);
-        case 8: return launch_chain<8>(f, b, g, in_view, s, emit);
+        case 1: return launch_chain<1>(b, g, s, phase);
+        case 2: return launch_chain<2>(b, g, s, phase);
+        case 4: return launch_chain<4>(b, g, s, phase);
+        case 8: return launch_chain<8>(b, g, s, phase);
     }
     return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
 }
@@ -240,11 +247,10 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     g.K = K;
     g.Bpad = 32u * K;
     g.R = g.span + shf::kBatchCols;
-    g.VS = (4u * K + g.Bpad);
-    if (((g.VS / 4u) & 1u) == 0u) g.VS += 4u;
+    g.VS = g.Bpad;
     // rows per CTA: as many as fit the shared memory, at most 16 (and at most H)
     uint32_t ty = std::min<uint32_t>(16u, H);
-    auto smem_of = [&](uint32_t t) { return (size_t)t * g.R * g.VS + (size_t)t * 2 * 32 * K * 4 + 32 * K * 2; };
+    auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
     while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
     if (smem_of(ty) > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "ring fits shared memory", "radius x biome count too large for one CTA");
@@ -259,7 +265,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(b->vstart.ensure(cells * 2));
     SHF_CUDA(b->dict.ensure((size_t)n_chunks * g.Bpad * 2));
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
-    SHF_CUDA(b->basemask.ensure((size_t)n_chunks * g.T * g.PW * K * 4));
+    SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * g.PW * K * 4));
     SHF_CUDA(b->rowtotal.ensure((size_t)n_chunks * H * 4));
     SHF_CUDA(b->rowbase.ensure((size_t)n_chunks * H * 4));
     SHF_CUDA(b->chunktotal.ensure((size_t)n_chunks * 8));
@@ -273,7 +279,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(cudaGetLastError());
 
     // ---- vertical scan + counting march ----
-    int st = dispatch_chain(K, f, b, g, in_dev, s, false);
+    int st = dispatch_chain(K, b, g, s, 0);
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(3, s));
     shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
@@ -298,7 +304,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
 
     // ---- emitting march ----
     SHF_CUDA(b->mark(5, s));
-    st = dispatch_chain(K, f, b, g, in_dev, s, true);
+    st = dispatch_chain(K, b, g, s, 1);
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(6, s));
     b->ev_valid = g_profiling != 0;

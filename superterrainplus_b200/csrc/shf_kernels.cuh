@@ -39,7 +39,7 @@ struct Geo {
     uint32_t TY, T;                // rows per march CTA, tiles per chunk
     uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
     uint32_t R;                    // ring columns = span + kBatchCols
-    uint32_t VS;                   // ring slot stride in bytes: 4*K mask + Bpad counts (+4 so that VS/4 is odd)
+    uint32_t VS;                   // count vector stride in the ring (= Bpad)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
 };
 
@@ -127,14 +127,15 @@ __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint3
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// vertical scan: vstart map + per-tile base count vectors
+// vertical scan: vstart map, per-tile base count vectors, per-(row, column) presence masks
 // ------------------------------------------------------------------------------------------------------------------
 // Per thread (= column) private shared memory: hist u8[Bpad] | last u16[Bpad] | start u16[Bpad], stride 5*Bpad+4 bytes
 // (an odd number of words, so that equal offsets of neighbouring threads fall into different banks).
+// colmask(n, y, c) = K words, bit b of word k set iff compact id 32k+b occurs in column c, rows [y, y+2r].
 template <int K>
 __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint16_t* __restrict__ cmap,
                                                               uint16_t* __restrict__ vstart, uint8_t* __restrict__ base,
-                                                              uint32_t* __restrict__ basemask) {
+                                                              uint32_t* __restrict__ colmask) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int Bpad = 32 * K;
     constexpr int kStride = 5 * Bpad + 4;
@@ -155,7 +156,9 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     for (int k = 0; k < K; k++) mask[k] = 0u;
     const uint16_t* col = cmap + (size_t)n * g.PH * g.P + c;
     uint16_t* vcol = vstart + (size_t)n * g.PH * g.P + c;
+    uint32_t* mcol = colmask + ((size_t)n * g.H * g.PW + c) * K;
     const uint32_t span = g.span, two_r = 2u * g.r;
+    uint32_t next_tile_row = 0u, tile = 0u;
     for (uint32_t p = 0; p < g.PH; p++) {
         const uint32_t s = col[(size_t)p * g.P];
         const uint32_t l = last[s];
@@ -176,19 +179,74 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             }
         }
         if (p >= two_r) {
-            const uint32_t y = p - two_r;
-            if (y < g.H && y % g.TY == 0u) {
-                const uint32_t t = y / g.TY;
-                const size_t slot = ((size_t)n * g.T + t) * g.PW + c;
+            const uint32_t y = p - two_r;  // the window [y, y+2r] is complete
+#pragma unroll
+            for (int k = 0; k < K; k++) mcol[(size_t)y * g.PW * K + k] = mask[k];
+            if (y == next_tile_row) {
+                const size_t slot = ((size_t)n * g.T + tile) * g.PW + c;
                 uint4* dst = reinterpret_cast<uint4*>(base + slot * Bpad);
                 const uint32_t* hw = reinterpret_cast<const uint32_t*>(hist);
 #pragma unroll
                 for (int q = 0; q < 2 * K; q++) dst[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-#pragma unroll
-                for (int k = 0; k < K; k++) basemask[slot * K + k] = mask[k];
+                tile++;
+                next_tile_row += g.TY;
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bins per row without building any histogram: a pixel's bin count is the popcount of the OR of its window's column
+// masks (the count is order-free, so this is exact by construction). One warp per row; the sliding OR of width 2r+1 is
+// assembled from power-of-two windows (binary decomposition of the width) in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) rowcount_kernel(Geo g, const uint32_t* __restrict__ colmask,
+                                                       uint32_t* __restrict__ rowtotal) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t y = blockIdx.x * (blockDim.x >> 5) + warp, n = blockIdx.y;
+    if (y >= g.H) return;
+    const uint32_t PW = g.PW;
+    uint32_t* powr = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 2 * PW * K;  // window of length 2^k at i
+    uint32_t* acc = powr + (size_t)PW * K;                                          // window of length L at i
+    const uint32_t* src = colmask + ((size_t)n * g.H + y) * PW * K;
+    for (uint32_t i = lane; i < PW * K; i += 32u) {
+        powr[i] = src[i];
+        acc[i] = 0u;
+    }
+    __syncwarp();
+    uint32_t L = 0u;
+    for (uint32_t bit = 1u; bit <= g.span; bit <<= 1) {
+        if (g.span & bit) {  // acc(i) |= pow(i + L): extends every window from length L to L + bit
+            for (uint32_t i = lane; i + L < PW; i += 32u)
+#pragma unroll
+                for (int k = 0; k < K; k++) acc[i * K + k] |= powr[(i + L) * K + k];
+            L += bit;
+            __syncwarp();
+        }
+        if ((bit << 1) <= g.span) {  // pow(i) |= pow(i + bit), in place: read everything first, then write
+            uint32_t tmp[K];
+            for (uint32_t i0 = 0u; i0 + bit < PW; i0 += 32u) {
+                const uint32_t i = i0 + lane;
+                const bool ok = i + bit < PW;
+#pragma unroll
+                for (int k = 0; k < K; k++) tmp[k] = ok ? powr[(i + bit) * K + k] : 0u;
+                __syncwarp();
+                if (ok) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) powr[i * K + k] |= tmp[k];
+                }
+                __syncwarp();
+            }
+        }
+    }
+    uint32_t total = 0u;
+    for (uint32_t x = lane; x < g.W; x += 32u)
+#pragma unroll
+        for (int k = 0; k < K; k++) total += __popc(acc[x * K + k]);
+    total = __reduce_add_sync(kFull, total);
+    if (lane == 0u) rowtotal[(size_t)n * g.H + y] = total;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -209,135 +267,157 @@ __device__ __forceinline__ bool test_bit(const uint32_t (&words)[K], uint32_t s)
     return hit;
 }
 
-// A list entry is one register pair per lane and set: item = (sample value << 16) | compact id, cnt = window count.
+// Shared memory of a march CTA (TY rows, one warp per row):
+//   cring[TY][R][32K]  u8   vertical window counts of the last R = 2r+1+32 columns, per row, indexed by compact id
+//   mring[TY][R][K]    u32  presence masks of the same columns
+//   scratch[TY][2][32K] u32 per-warp staging for list compaction / birth ordering
+//   sdict[32K]         u16  compact id -> sample value
+// Per batch of 32 columns: (P) the CTA produces the batch's count vectors and masks, (C) every warp advances its row.
+// (P) is done "transposed": a group of LPC lanes owns one column, holds its count vector in registers (one 32-bit word
+// = 4 biome counters per lane), starts from the tile's base vector and slides it down row by row, storing one slot per
+// row; that keeps the production balanced across warps and free of shared-memory read-modify-writes.
+//
+// A list entry is one register triple per lane and set: id = compact id, hi = sample value, cnt = window count.
 // Entry e = k*32 + lane, valid iff e < n. The list order is the reference accumulator's bin order.
-template <int K, bool EMIT>
+template <int K>
 __global__ void __launch_bounds__(512, 1)
     march_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint16_t* __restrict__ vstart,
-                 const uint8_t* __restrict__ base, const uint32_t* __restrict__ basemask,
-                 const uint16_t* __restrict__ dict, uint32_t dict_stride, uint32_t* __restrict__ rowtotal,
-                 const uint32_t* __restrict__ rowbase, const uint64_t* __restrict__ chunkbase,
-                 uint2* __restrict__ bins, uint32_t* __restrict__ hso) {
+                 const uint8_t* __restrict__ base, const uint32_t* __restrict__ colmask,
+                 const uint16_t* __restrict__ dict, uint32_t dict_stride, const uint32_t* __restrict__ rowbase,
+                 const uint64_t* __restrict__ chunkbase, uint2* __restrict__ bins, uint32_t* __restrict__ hso) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int Bpad = 32 * K;
-    constexpr int E = 32 * K;  // list capacity
-    const uint32_t TY = g.TY, R = g.R, VS = g.VS, span = g.span, two_r = 2u * g.r;
+    constexpr int CS = 32 * K;                // bytes per count vector
+    constexpr int E = 32 * K;                 // list capacity
+    constexpr int LPC = (K == 1) ? 8 : 16;    // lanes per column in the produce phase
+    constexpr int WPL = (8 * K) / LPC;        // 32-bit count words per lane
+    constexpr int UPW = 32 / LPC;             // columns a warp produces at a time
+    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
     const uint32_t y0 = tile * TY, y = y0 + warp;
     const bool row_active = y < g.H;
 
-    uint8_t* ring = smem;                                                         // [TY][R][VS]
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + (size_t)TY * R * VS);  // [TY][2][E]
-    uint16_t* sdict = reinterpret_cast<uint16_t*>(scratch + (size_t)TY * 2 * E);  // [E]
+    uint8_t* cring = smem;
+    uint32_t* mring = reinterpret_cast<uint32_t*>(smem + (size_t)TY * R * CS);
+    uint32_t* scratch = mring + (size_t)TY * R * K;
+    uint16_t* sdict = reinterpret_cast<uint16_t*>(scratch + (size_t)TY * 2 * E);
     uint32_t* sA = scratch + (size_t)warp * 2 * E;
     uint32_t* sB = sA + E;
     for (uint32_t i = threadIdx.x; i < (uint32_t)E; i += blockDim.x)
         sdict[i] = (i < dict_stride) ? dict[(size_t)n_chunk * dict_stride + i] : (uint16_t)0;
 
-    uint8_t* myring = ring + (size_t)warp * R * VS;
+    uint8_t* crow = cring + (size_t)warp * R * CS;
+    uint32_t* mrow = mring + (size_t)warp * R * K;
     const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
     const uint16_t* vs = vstart + (size_t)n_chunk * g.PH * g.P;
+    const uint32_t* cmask_row = colmask + ((size_t)n_chunk * g.H + (row_active ? y : 0u)) * PW * K;
 
     // ordered bin list of this row
-    uint32_t item[K], cnt[K], listmask[K];
+    uint32_t id[K], hi[K], cnt[K], listmask[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        item[k] = 0u;
+        id[k] = 0u;
+        hi[k] = 0u;
         cnt[k] = 0u;
         listmask[k] = 0u;
     }
     uint32_t n = 0u;       // bins in the list
     uint32_t rowpos = 0u;  // bins emitted so far in this row
     uint32_t hso_reg = 0u;
-    size_t out0 = 0;
-    if (EMIT && row_active) out0 = (size_t)chunkbase[n_chunk] + rowbase[(size_t)n_chunk * g.H + y];
-    const uint32_t first_row_bins = (EMIT && row_active) ? rowbase[(size_t)n_chunk * g.H + y] : 0u;
+    const uint32_t row_first = row_active ? rowbase[(size_t)n_chunk * g.H + y] : 0u;
+    uint2* dst = bins + (row_active ? (size_t)chunkbase[n_chunk] + row_first : (size_t)0) + lane;
+    uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
     const float inv = g.inv_total;
 
-    uint32_t in_slot = 0u;  // ring slot of column c
-    for (uint32_t cb = 0u; cb < g.PW; cb += kBatchCols) {
+    // produce-phase roles
+    const uint32_t sub = lane % LPC;                    // my position inside the column group
+    const uint32_t units = TY * UPW;
+    const uint32_t group_base = lane - sub;
+    const uint32_t tile_rows = min(TY, g.H - y0);
+
+    uint32_t slot0 = 0u;  // ring slot of column cb
+    for (uint32_t cb = 0u; cb < PW; cb += kBatchCols) {
         __syncthreads();  // every warp is done with the slots about to be overwritten (and sdict is loaded)
-        // ---- produce: vertical window counts of columns [cb, cb+32) for this warp's row (lane = column) ----
-        {
-            const uint32_t c = cb + lane;
-            if (row_active && c < g.PW) {
-                uint32_t slot_idx = in_slot + lane;
-                if (slot_idx >= R) slot_idx -= R;
-                uint8_t* slot = myring + (size_t)slot_idx * VS;
-                uint32_t* slot_w = reinterpret_cast<uint32_t*>(slot);
-                uint8_t* sc = slot + 4 * K;
-                const size_t bslot = ((size_t)n_chunk * g.T + tile) * g.PW + c;
-                const uint4* bsrc = reinterpret_cast<const uint4*>(base + bslot * Bpad);
+        // ---------------- (P) produce columns [cb, cb+32) ----------------
+        for (uint32_t cu0 = warp * UPW; cu0 < (uint32_t)kBatchCols; cu0 += units) {  // warp-uniform trip count
+            const uint32_t cu = cu0 + lane / LPC;
+            const bool live = cu < (uint32_t)kBatchCols && cb + cu < PW;
+            const uint32_t c = live ? cb + cu : PW - 1u;
+            uint32_t slot = slot0 + cu;
+            if (slot >= R) slot -= R;
+            // tile base vector: word (sub + LPC*j) of the column's 8K words
+            uint32_t words[WPL];
+            const uint32_t* bsrc =
+                reinterpret_cast<const uint32_t*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS);
 #pragma unroll
-                for (int q = 0; q < 2 * K; q++) {
-                    const uint4 v = bsrc[q];
-                    slot_w[K + 4 * q + 0] = v.x;
-                    slot_w[K + 4 * q + 1] = v.y;
-                    slot_w[K + 4 * q + 2] = v.z;
-                    slot_w[K + 4 * q + 3] = v.w;
+            for (int j = 0; j < WPL; j++) words[j] = bsrc[sub + LPC * j];
+            // samples entering / leaving the vertical window when it moves from tile row i to i+1: lane `sub` preloads
+            // rows i = sub (+ LPC)
+            constexpr int RPL = (16 + LPC - 1) / LPC;
+            uint32_t s_in[RPL], s_out[RPL];
+#pragma unroll
+            for (int q = 0; q < RPL; q++) {
+                const uint32_t i = sub + LPC * q;
+                const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
+                s_in[q] = cm[(size_t)pi * g.P + c];
+                s_out[q] = cm[(size_t)po * g.P + c];
+            }
+            uint8_t* out = cring + (size_t)slot * CS + sub * 4u;
+            for (uint32_t i = 0u; i < tile_rows; i++) {
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < WPL; j++) *reinterpret_cast<uint32_t*>(out + LPC * 4 * j) = words[j];
                 }
-                uint32_t mask[K];
+                out += (size_t)R * CS;
+                uint32_t a = 0u, o = 0u;
 #pragma unroll
-                for (int k = 0; k < K; k++) mask[k] = basemask[bslot * K + k];
-                // slide the vertical window down from the tile's first row to this warp's row
-                for (uint32_t i0 = 0u; i0 < warp; i0 += 8u) {
-                    uint32_t sin[8], sout[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint32_t i = i0 + j;
-                        if (i < warp) {
-                            sin[j] = cm[(size_t)(y0 + i + span) * g.P + c];
-                            sout[j] = cm[(size_t)(y0 + i) * g.P + c];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint32_t i = i0 + j;
-                        if (i < warp) {
-                            const uint32_t a = sin[j], o = sout[j];
-                            if (++sc[a] == 1) {
-#pragma unroll
-                                for (int k = 0; k < K; k++)
-                                    if ((a >> 5) == (uint32_t)k) mask[k] |= 1u << (a & 31u);
-                            }
-                            if (--sc[o] == 0) {
-#pragma unroll
-                                for (int k = 0; k < K; k++)
-                                    if ((o >> 5) == (uint32_t)k) mask[k] &= ~(1u << (o & 31u));
-                            }
-                        }
+                for (int q = 0; q < RPL; q++) {
+                    const uint32_t av = __shfl_sync(kFull, s_in[q], group_base + (i % LPC));
+                    const uint32_t ov = __shfl_sync(kFull, s_out[q], group_base + (i % LPC));
+                    if ((uint32_t)q == i / LPC) {
+                        a = av;
+                        o = ov;
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < K; k++) slot_w[k] = mask[k];
+                for (int j = 0; j < WPL; j++) {
+                    const uint32_t me = sub + LPC * j;
+                    words[j] += ((a >> 2) == me ? (1u << ((a & 3u) * 8u)) : 0u) - ((o >> 2) == me ? (1u << ((o & 3u) * 8u)) : 0u);
+                }
             }
         }
+        // this row's presence masks of the batch (lane = column)
+        if (row_active && cb + lane < PW) {
+            uint32_t slot = slot0 + lane;
+            if (slot >= R) slot -= R;
+#pragma unroll
+            for (int k = 0; k < K; k++) mrow[(size_t)slot * K + k] = cmask_row[(size_t)(cb + lane) * K + k];
+        }
         __syncthreads();
-        // ---- consume: advance this row's window over the batch ----
+        // ---------------- (C) advance this row's window over the batch ----------------
         if (row_active) {
-            const uint32_t c_end = min(cb + (uint32_t)kBatchCols, g.PW);
+            const uint32_t c_end = min(cb + (uint32_t)kBatchCols, PW);
+            uint32_t in_slot = slot0;
             for (uint32_t c = cb; c < c_end; c++) {
-                const uint8_t* sin = myring + (size_t)in_slot * VS;
-                const uint32_t* sin_w = reinterpret_cast<const uint32_t*>(sin);
-                const uint8_t* sin_c = sin + 4 * K;
+                const uint8_t* pin = crow + (size_t)in_slot * CS;
+                const uint32_t* pm = mrow + (size_t)in_slot * K;
                 uint32_t out_slot = in_slot + R - span;  // column c - span
                 if (out_slot >= R) out_slot -= R;
-                const uint8_t* sout_c = myring + (size_t)out_slot * VS + 4 * K;
+                const uint8_t* pout = crow + (size_t)out_slot * CS;
                 const bool has_out = c >= span;
-                bool event = false;
+                bool deadp = false;
+                uint32_t bornany = 0u;
                 uint32_t born[K];
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                    const uint32_t id = item[k] & 0xFFFFu;
-                    uint32_t v = cnt[k] + sin_c[id];
-                    if (has_out) v -= sout_c[id];
+                    uint32_t v = cnt[k] + pin[id[k]];
+                    if (has_out) v -= pout[id[k]];
                     cnt[k] = v;
-                    born[k] = sin_w[k] & ~listmask[k];
-                    const bool dead = (k * 32 + lane < n) && v == 0u;
-                    event |= (born[k] != 0u) | (__ballot_sync(kFull, dead) != 0u);
+                    born[k] = pm[k] & ~listmask[k];
+                    bornany |= born[k];
+                    deadp |= ((uint32_t)(k * 32) + lane < n) && v == 0u;
                 }
-                if (event) {
+                if (__any_sync(kFull, deadp) || bornany != 0u) {
                     // ---------------- slow path: bins die and/or are born ----------------
                     // (1) drop dead bins, keeping the order of the survivors (SHF.cpp:435-445)
                     {
@@ -345,11 +425,11 @@ __global__ void __launch_bounds__(512, 1)
                         __syncwarp();
 #pragma unroll
                         for (int k = 0; k < K; k++) {
-                            const bool alive = (k * 32 + lane < n) && cnt[k] != 0u;
+                            const bool alive = ((uint32_t)(k * 32) + lane < n) && cnt[k] != 0u;
                             const unsigned am = __ballot_sync(kFull, alive);
                             if (alive) {
                                 const uint32_t idx = keep_base + __popc(am & lanemask_lt());
-                                sA[idx] = item[k];
+                                sA[idx] = (hi[k] << 16) | id[k];
                                 sB[idx] = cnt[k];
                             }
                             keep_base += __popc(am);
@@ -361,7 +441,9 @@ __global__ void __launch_bounds__(512, 1)
                             for (int k = 0; k < K; k++) {
                                 const uint32_t e = k * 32 + lane;
                                 if (e < n) {
-                                    item[k] = sA[e];
+                                    const uint32_t packed = sA[e];
+                                    id[k] = packed & 0xFFFFu;
+                                    hi[k] = packed >> 16;
                                     cnt[k] = sB[e];
                                 }
                             }
@@ -392,7 +474,7 @@ __global__ void __launch_bounds__(512, 1)
                             if (first) {
                                 const uint32_t idx = found + __popc(fm & lanemask_lt());
                                 sA[idx] = ((uint32_t)sdict[s] << 16) | s;
-                                sB[idx] = ((uint32_t)vs[at] << 16) | (uint32_t)sin_c[s];
+                                sB[idx] = ((uint32_t)vs[at] << 16) | (uint32_t)pin[s];
                             }
                             found += __popc(fm);
 #pragma unroll
@@ -408,14 +490,14 @@ __global__ void __launch_bounds__(512, 1)
                         for (int k = 0; k < K; k++) {
                             const uint32_t idx = k * 32 + lane;
                             rank[k] = idx;
+                            ra[k] = 0u;
+                            rb[k] = 0u;
                             if (idx < nb) {
                                 ra[k] = sA[idx];
                                 rb[k] = sB[idx];
-                                if (EMIT) {
-                                    uint32_t rk = 0u;
-                                    for (uint32_t i = 0u; i < nb; i++) rk += (sB[i] >> 16) < (rb[k] >> 16);
-                                    rank[k] = rk;
-                                }
+                                uint32_t rk = 0u;
+                                for (uint32_t i = 0u; i < nb; i++) rk += (sB[i] >> 16) < (rb[k] >> 16);
+                                rank[k] = rk;
                             }
                         }
                         __syncwarp();
@@ -431,7 +513,9 @@ __global__ void __launch_bounds__(512, 1)
                         for (int k = 0; k < K; k++) {
                             const uint32_t e = k * 32 + lane;
                             if (e >= n && e < n + nb) {
-                                item[k] = sA[e - n];
+                                const uint32_t packed = sA[e - n];
+                                id[k] = packed & 0xFFFFu;
+                                hi[k] = packed >> 16;
                                 cnt[k] = sB[e - n] & 0xFFFFu;
                             }
                         }
@@ -444,8 +528,7 @@ __global__ void __launch_bounds__(512, 1)
                         uint32_t mine = 0u;
 #pragma unroll
                         for (int k = 0; k < K; k++) {
-                            const uint32_t id = item[k] & 0xFFFFu;
-                            if ((uint32_t)(k * 32) + lane < n && (id >> 5) == (uint32_t)kk) mine |= 1u << (id & 31u);
+                            if ((uint32_t)(k * 32) + lane < n && (id[k] >> 5) == (uint32_t)kk) mine |= 1u << (id[k] & 31u);
                         }
                         listmask[kk] = __reduce_or_sync(kFull, mine);
                     }
@@ -453,33 +536,26 @@ __global__ void __launch_bounds__(512, 1)
                 // ---------------- emit pixel x = c - 2r ----------------
                 if (c >= two_r) {
                     const uint32_t x = c - two_r;
-                    if (EMIT) {
-                        uint2* dst = bins + out0 + rowpos;
 #pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const uint32_t e = k * 32 + lane;
-                            if (e < n) {
-                                const float w = __fmul_rn(__uint2float_rn(cnt[k]), inv);
-                                dst[e] = make_uint2(item[k] >> 16, __float_as_uint(w));
-                            }
-                        }
-                        if ((x & 31u) == lane) hso_reg = first_row_bins + rowpos;
-                        if ((x & 31u) == 31u || x == g.W - 1u) {
-                            if (lane <= (x & 31u))
-                                hso[(size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)y * g.W + (x & ~31u) + lane] =
-                                    hso_reg;
+                    for (int k = 0; k < K; k++) {
+                        if ((uint32_t)(k * 32) + lane < n) {
+                            const float w = __fmul_rn(__uint2float_rn(cnt[k]), inv);
+                            dst[k * 32] = make_uint2(hi[k], __float_as_uint(w));
                         }
                     }
+                    dst += n;
+                    if ((x & 31u) == lane) hso_reg = row_first + rowpos;
                     rowpos += n;
+                    if ((x & 31u) == 31u || x == g.W - 1u) {
+                        if (lane <= (x & 31u)) hso_row[(x & ~31u) + lane] = hso_reg;
+                    }
                 }
                 in_slot = (in_slot + 1u == R) ? 0u : in_slot + 1u;
             }
-        } else {
-            in_slot += kBatchCols;
-            if (in_slot >= R) in_slot -= R;
         }
+        slot0 += kBatchCols;
+        if (slot0 >= R) slot0 -= R;
     }
-    if (!EMIT && row_active && lane == 0u) rowtotal[(size_t)n_chunk * g.H + y] = rowpos;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -133,7 +133,7 @@ namespace {
 using shf::Geo;
 
 size_t march_smem(uint32_t ty, uint32_t R, int K) {
-    return (size_t)ty * R * 32 * K + (size_t)ty * R * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2;
+    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2;
 }
 
 // phase 0: vertical scan + bins per row; phase 1: the emitting march
@@ -162,7 +162,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     } else {
         const size_t smem = march_smem(g.TY, g.R, K);
         SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), g.TY * 32, smem, s>>>(
+        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + 1) * 32, smem, s>>>(
             g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
             b->dict.as<uint16_t>(), 32 * K, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(),
             b->hso.as<uint32_t>());
@@ -246,11 +246,16 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
     g.K = K;
     g.Bpad = 32u * K;
-    g.R = g.span + shf::kBatchCols;
+    g.stages = 3u;
+    g.R = g.span + shf::kMarchNB * g.stages;
     g.VS = g.Bpad;
     // rows per CTA: as many as fit the shared memory, at most 16 (and at most H)
     uint32_t ty = std::min<uint32_t>(16u, H);
     auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
+    if (smem_of(ty) > f->smem_optin) {  // prefer two look-ahead batches over fewer rows per CTA
+        g.stages = 2u;
+        g.R = g.span + shf::kMarchNB * g.stages;
+    }
     while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
     if (smem_of(ty) > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "ring fits shared memory", "radius x biome count too large for one CTA");

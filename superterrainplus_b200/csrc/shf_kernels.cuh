@@ -24,7 +24,6 @@
 namespace shf {
 
 constexpr int kDictWords = 2048;      // 65536 possible sample values / 32
-constexpr int kBatchCols = 32;        // NB: columns produced per phase of the march kernel (one per lane)
 constexpr int kVscanThreads = 64;     // columns per CTA in vscan
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kNoRow = 0xFFFFu;
@@ -38,7 +37,8 @@ struct Geo {
     uint64_t in_chunk_stride;
     uint32_t TY, T;                // rows per march CTA, tiles per chunk
     uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
-    uint32_t R;                    // ring columns = span + kBatchCols
+    uint32_t R;                    // ring columns = span + 16 * stages
+    uint32_t stages;               // batches the march producer may run ahead (2 or 3)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
 };
@@ -267,52 +267,115 @@ __device__ __forceinline__ bool test_bit(const uint32_t (&words)[K], uint32_t s)
     return hit;
 }
 
-// Shared memory of a march CTA (TY rows, one warp per row):
-//   cring[TY][R][32K]  u8   vertical window counts of the last R = 2r+1+32 columns, per row, indexed by compact id
-//   mring[TY][R][K]    u32  presence masks of the same columns
-//   scratch[TY][2][32K] u32 per-warp staging for list compaction / birth ordering
-//   sdict[32K]         u16  compact id -> sample value
-// Per batch of 32 columns: (P) the CTA produces the batch's count vectors and masks, (C) every warp advances its row.
-// (P) is done "transposed": a group of LPC lanes owns one column, holds its count vector in registers (one 32-bit word
-// = 4 biome counters per lane), starts from the tile's base vector and slides it down row by row, storing one slot per
-// row; that keeps the production balanced across warps and free of shared-memory read-modify-writes.
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Shared memory of a march CTA (TY consumer warps = TY rows, plus one producer warp):
+//   cring[TY][R][32K]   u8   vertical window counts of the last R = 2r+1 + NB*stages columns, per row, by compact id
+//   mbuf[TY][NB][K]     u32  presence masks of the batch being consumed, per row
+//   scratch[TY][2][32K] u32  per-warp staging for list compaction / birth ordering
+//   sdict[32K]          u16  compact id -> sample value
+// The producer warp runs `stages` batches of NB = 16 columns ahead of the consumers. For a column it keeps the count
+// vector in registers (2K lanes x 16 bytes), starts from the tile's base vector, and walks down the tile's rows: store
+// the row's slot (one 128-bit store per lane, neighbouring columns fill one 128-byte line), then apply the one sample
+// entering and the one leaving the vertical window. Hand-over uses named barriers: FULL(s) producer -> consumers,
+// EMPTY(s) consumers -> producer, s = batch % stages.
 //
-// A list entry is one register triple per lane and set: id = compact id, hi = sample value, cnt = window count.
-// Entry e = k*32 + lane, valid iff e < n. The list order is the reference accumulator's bin order.
+// A consumer warp keeps its row's ordered bin list in registers: entry e = k*32 + lane (valid iff e < n) is the triple
+// id (compact id) / hi (sample value) / cnt (window count). A step adds column c, removes column c - (2r+1), handles
+// bin deaths/births if there are any (slow path), and emits pixel x = c - 2r. In the steady state four steps are done
+// at once when none of them has a death or birth.
+constexpr int kMarchNB = 16;
+
 template <int K>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(544, 1)
     march_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint16_t* __restrict__ vstart,
                  const uint8_t* __restrict__ base, const uint32_t* __restrict__ colmask,
                  const uint16_t* __restrict__ dict, uint32_t dict_stride, const uint32_t* __restrict__ rowbase,
                  const uint64_t* __restrict__ chunkbase, uint2* __restrict__ bins, uint32_t* __restrict__ hso) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int CS = 32 * K;                // bytes per count vector
-    constexpr int E = 32 * K;                 // list capacity
-    constexpr int LPC = (K == 1) ? 8 : 16;    // lanes per column in the produce phase
-    constexpr int WPL = (8 * K) / LPC;        // 32-bit count words per lane
-    constexpr int UPW = 32 / LPC;             // columns a warp produces at a time
-    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW;
+    constexpr int CS = 32 * K;  // bytes per count vector
+    constexpr int E = 32 * K;   // list capacity
+    constexpr int NB = kMarchNB;
+    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW, stages = g.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
-    const uint32_t y0 = tile * TY, y = y0 + warp;
-    const bool row_active = y < g.H;
+    const uint32_t y0 = tile * TY;
+    const uint32_t all_threads = (TY + 1u) * 32u;
+    const uint32_t n_batches = (PW + NB - 1u) / NB;
 
     uint8_t* cring = smem;
-    uint32_t* mring = reinterpret_cast<uint32_t*>(smem + (size_t)TY * R * CS);
-    uint32_t* scratch = mring + (size_t)TY * R * K;
+    uint32_t* mbuf_all = reinterpret_cast<uint32_t*>(smem + (size_t)TY * R * CS);
+    uint32_t* scratch = mbuf_all + (size_t)TY * NB * K;
     uint16_t* sdict = reinterpret_cast<uint16_t*>(scratch + (size_t)TY * 2 * E);
-    uint32_t* sA = scratch + (size_t)warp * 2 * E;
-    uint32_t* sB = sA + E;
     for (uint32_t i = threadIdx.x; i < (uint32_t)E; i += blockDim.x)
         sdict[i] = (i < dict_stride) ? dict[(size_t)n_chunk * dict_stride + i] : (uint16_t)0;
-
-    uint8_t* crow = cring + (size_t)warp * R * CS;
-    uint32_t* mrow = mring + (size_t)warp * R * K;
+    __syncthreads();
     const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
+
+    if (warp == TY) {
+        // =============================== producer warp ===============================
+        constexpr int LPC = 2 * K;       // lanes per column, 16 bytes each
+        constexpr int CPP = 32 / LPC;    // columns per pass
+        const uint32_t part = lane % LPC, colq = lane / LPC;
+        const uint32_t tile_rows = min(TY, g.H - y0);
+        uint32_t slot0 = 0u;  // ring slot of the batch's first column
+        for (uint32_t b = 0u; b < n_batches; b++) {
+            const uint32_t s = b % stages, cb = b * NB;
+            if (b >= stages) named_bar_sync(1u + stages + s, all_threads);  // EMPTY(s): batch b - stages is consumed
+#pragma unroll 1
+            for (uint32_t pass = 0u; pass < (uint32_t)(NB / CPP); pass++) {
+                const uint32_t cu = pass * CPP + colq;
+                const bool live = cb + cu < PW;
+                const uint32_t c = live ? cb + cu : PW - 1u;
+                uint32_t slot = slot0 + cu;
+                if (slot >= R) slot -= R;
+                uint4 v = *reinterpret_cast<const uint4*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS + part * 16u);
+                // samples entering / leaving the vertical window when it moves from tile row i to i+1
+                uint32_t sa[16], so[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
+                    sa[i] = cm[(size_t)pi * g.P + c];
+                    so[i] = cm[(size_t)po * g.P + c];
+                }
+                uint8_t* out = cring + (size_t)slot * CS + part * 16u;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if ((uint32_t)i < tile_rows) {
+                        if (live) *reinterpret_cast<uint4*>(out) = v;
+                        out += (size_t)R * CS;
+                        const uint32_t wa = (sa[i] >> 2) - part * 4u, ia = 1u << ((sa[i] & 3u) * 8u);
+                        const uint32_t wo = (so[i] >> 2) - part * 4u, io = 1u << ((so[i] & 3u) * 8u);
+                        v.x += (wa == 0u ? ia : 0u) - (wo == 0u ? io : 0u);
+                        v.y += (wa == 1u ? ia : 0u) - (wo == 1u ? io : 0u);
+                        v.z += (wa == 2u ? ia : 0u) - (wo == 2u ? io : 0u);
+                        v.w += (wa == 3u ? ia : 0u) - (wo == 3u ? io : 0u);
+                    }
+                }
+            }
+            __threadfence_block();
+            named_bar_arrive(1u + s, all_threads);  // FULL(s)
+            slot0 += NB;
+            if (slot0 >= R) slot0 -= R;
+        }
+        return;
+    }
+
+    // =============================== consumer warps ===============================
+    const uint32_t y = y0 + warp;
+    const bool row_active = y < g.H;
+    uint8_t* crow = cring + (size_t)warp * R * CS;
+    uint32_t* mbuf = mbuf_all + (size_t)warp * NB * K;
+    uint32_t* sA = scratch + (size_t)warp * 2 * E;
+    uint32_t* sB = sA + E;
     const uint16_t* vs = vstart + (size_t)n_chunk * g.PH * g.P;
     const uint32_t* cmask_row = colmask + ((size_t)n_chunk * g.H + (row_active ? y : 0u)) * PW * K;
 
-    // ordered bin list of this row
     uint32_t id[K], hi[K], cnt[K], listmask[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -329,232 +392,240 @@ __global__ void __launch_bounds__(512, 1)
     uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
     const float inv = g.inv_total;
 
-    // produce-phase roles
-    const uint32_t sub = lane % LPC;                    // my position inside the column group
-    const uint32_t units = TY * UPW;
-    const uint32_t group_base = lane - sub;
-    const uint32_t tile_rows = min(TY, g.H - y0);
-
-    uint32_t slot0 = 0u;  // ring slot of column cb
-    for (uint32_t cb = 0u; cb < PW; cb += kBatchCols) {
-        __syncthreads();  // every warp is done with the slots about to be overwritten (and sdict is loaded)
-        // ---------------- (P) produce columns [cb, cb+32) ----------------
-        for (uint32_t cu0 = warp * UPW; cu0 < (uint32_t)kBatchCols; cu0 += units) {  // warp-uniform trip count
-            const uint32_t cu = cu0 + lane / LPC;
-            const bool live = cu < (uint32_t)kBatchCols && cb + cu < PW;
-            const uint32_t c = live ? cb + cu : PW - 1u;
-            uint32_t slot = slot0 + cu;
-            if (slot >= R) slot -= R;
-            // tile base vector: word (sub + LPC*j) of the column's 8K words
-            uint32_t words[WPL];
-            const uint32_t* bsrc =
-                reinterpret_cast<const uint32_t*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS);
-#pragma unroll
-            for (int j = 0; j < WPL; j++) words[j] = bsrc[sub + LPC * j];
-            // samples entering / leaving the vertical window when it moves from tile row i to i+1: lane `sub` preloads
-            // rows i = sub (+ LPC)
-            constexpr int RPL = (16 + LPC - 1) / LPC;
-            uint32_t s_in[RPL], s_out[RPL];
-#pragma unroll
-            for (int q = 0; q < RPL; q++) {
-                const uint32_t i = sub + LPC * q;
-                const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
-                s_in[q] = cm[(size_t)pi * g.P + c];
-                s_out[q] = cm[(size_t)po * g.P + c];
-            }
-            uint8_t* out = cring + (size_t)slot * CS + sub * 4u;
-            for (uint32_t i = 0u; i < tile_rows; i++) {
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < WPL; j++) *reinterpret_cast<uint32_t*>(out + LPC * 4 * j) = words[j];
-                }
-                out += (size_t)R * CS;
-                uint32_t a = 0u, o = 0u;
-#pragma unroll
-                for (int q = 0; q < RPL; q++) {
-                    const uint32_t av = __shfl_sync(kFull, s_in[q], group_base + (i % LPC));
-                    const uint32_t ov = __shfl_sync(kFull, s_out[q], group_base + (i % LPC));
-                    if ((uint32_t)q == i / LPC) {
-                        a = av;
-                        o = ov;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    const uint32_t me = sub + LPC * j;
-                    words[j] += ((a >> 2) == me ? (1u << ((a & 3u) * 8u)) : 0u) - ((o >> 2) == me ? (1u << ((o & 3u) * 8u)) : 0u);
-                }
-            }
-        }
-        // this row's presence masks of the batch (lane = column)
-        if (row_active && cb + lane < PW) {
-            uint32_t slot = slot0 + lane;
-            if (slot >= R) slot -= R;
-#pragma unroll
-            for (int k = 0; k < K; k++) mrow[(size_t)slot * K + k] = cmask_row[(size_t)(cb + lane) * K + k];
-        }
-        __syncthreads();
-        // ---------------- (C) advance this row's window over the batch ----------------
+    uint32_t in_slot = 0u;                       // ring slot of column c
+    uint32_t out_slot = (R - span % R) % R;      // ring slot of column c - span (meaningful once c >= span)
+    for (uint32_t b = 0u; b < n_batches; b++) {
+        const uint32_t s = b % stages, cb = b * NB;
+        const uint32_t ce = min(cb + (uint32_t)NB, PW);
+        named_bar_sync(1u + s, all_threads);  // FULL(s)
         if (row_active) {
-            const uint32_t c_end = min(cb + (uint32_t)kBatchCols, PW);
-            uint32_t in_slot = slot0;
-            for (uint32_t c = cb; c < c_end; c++) {
-                const uint8_t* pin = crow + (size_t)in_slot * CS;
-                const uint32_t* pm = mrow + (size_t)in_slot * K;
-                uint32_t out_slot = in_slot + R - span;  // column c - span
-                if (out_slot >= R) out_slot -= R;
-                const uint8_t* pout = crow + (size_t)out_slot * CS;
-                const bool has_out = c >= span;
-                bool deadp = false;
-                uint32_t bornany = 0u;
-                uint32_t born[K];
+            if (lane < (uint32_t)NB && cb + lane < PW) {
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    uint32_t v = cnt[k] + pin[id[k]];
-                    if (has_out) v -= pout[id[k]];
-                    cnt[k] = v;
-                    born[k] = pm[k] & ~listmask[k];
-                    bornany |= born[k];
-                    deadp |= ((uint32_t)(k * 32) + lane < n) && v == 0u;
-                }
-                if (__any_sync(kFull, deadp) || bornany != 0u) {
-                    // ---------------- slow path: bins die and/or are born ----------------
-                    // (1) drop dead bins, keeping the order of the survivors (SHF.cpp:435-445)
-                    {
-                        uint32_t keep_base = 0u;
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const bool alive = ((uint32_t)(k * 32) + lane < n) && cnt[k] != 0u;
-                            const unsigned am = __ballot_sync(kFull, alive);
-                            if (alive) {
-                                const uint32_t idx = keep_base + __popc(am & lanemask_lt());
-                                sA[idx] = (hi[k] << 16) | id[k];
-                                sB[idx] = cnt[k];
-                            }
-                            keep_base += __popc(am);
-                        }
-                        __syncwarp();
-                        if (keep_base != n) {
-                            n = keep_base;
-#pragma unroll
-                            for (int k = 0; k < K; k++) {
-                                const uint32_t e = k * 32 + lane;
-                                if (e < n) {
-                                    const uint32_t packed = sA[e];
-                                    id[k] = packed & 0xFFFFu;
-                                    hi[k] = packed >> 16;
-                                    cnt[k] = sB[e];
-                                }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    // (2) append the bins born in column c, ordered by their vertical chain start (SHF.cpp:411-415:
-                    //     the column's own bin order is the order the horizontal pass inserts them in)
-                    uint32_t nb = 0u;
-#pragma unroll
-                    for (int k = 0; k < K; k++) nb += __popc(born[k]);
-                    if (nb) {
-                        uint32_t pending[K];
-#pragma unroll
-                        for (int k = 0; k < K; k++) pending[k] = born[k];
-                        uint32_t found = 0u;
-                        // walk the window rows of column c bottom-up, 32 rows at a time: the lowest occurrence of a
-                        // biome carries its chain start in vstart
-                        for (uint32_t blk = 0u; blk * 32u < span && found < nb; blk++) {
-                            const int32_t off = (int32_t)two_r - (int32_t)(blk * 32u + lane);
-                            const bool valid = off >= 0;
-                            const size_t at = (size_t)(y + (valid ? off : 0)) * g.P + c;
-                            const uint32_t s = valid ? (uint32_t)cm[at] : 0xFFFFu;
-                            const bool inpend = valid && test_bit<K>(pending, s);
-                            const unsigned same = __match_any_sync(kFull, s);
-                            const bool first = inpend && ((uint32_t)(__ffs(same) - 1) == lane);
-                            const unsigned fm = __ballot_sync(kFull, first);
-                            if (first) {
-                                const uint32_t idx = found + __popc(fm & lanemask_lt());
-                                sA[idx] = ((uint32_t)sdict[s] << 16) | s;
-                                sB[idx] = ((uint32_t)vs[at] << 16) | (uint32_t)pin[s];
-                            }
-                            found += __popc(fm);
-#pragma unroll
-                            for (int k = 0; k < K; k++) {
-                                const uint32_t mine = (first && (s >> 5) == (uint32_t)k) ? (1u << (s & 31u)) : 0u;
-                                pending[k] &= ~__reduce_or_sync(kFull, mine);
-                            }
-                        }
-                        __syncwarp();
-                        // rank by chain start row (unique per biome within a column)
-                        uint32_t ra[K], rb[K], rank[K];
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const uint32_t idx = k * 32 + lane;
-                            rank[k] = idx;
-                            ra[k] = 0u;
-                            rb[k] = 0u;
-                            if (idx < nb) {
-                                ra[k] = sA[idx];
-                                rb[k] = sB[idx];
-                                uint32_t rk = 0u;
-                                for (uint32_t i = 0u; i < nb; i++) rk += (sB[i] >> 16) < (rb[k] >> 16);
-                                rank[k] = rk;
-                            }
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            if ((uint32_t)(k * 32) + lane < nb) {
-                                sA[rank[k]] = ra[k];
-                                sB[rank[k]] = rb[k];
-                            }
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const uint32_t e = k * 32 + lane;
-                            if (e >= n && e < n + nb) {
-                                const uint32_t packed = sA[e - n];
-                                id[k] = packed & 0xFFFFu;
-                                hi[k] = packed >> 16;
-                                cnt[k] = sB[e - n] & 0xFFFFu;
-                            }
-                        }
-                        n += nb;
-                        __syncwarp();
-                    }
-                    // (3) membership mask of the list
-#pragma unroll
-                    for (int kk = 0; kk < K; kk++) {
-                        uint32_t mine = 0u;
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            if ((uint32_t)(k * 32) + lane < n && (id[k] >> 5) == (uint32_t)kk) mine |= 1u << (id[k] & 31u);
-                        }
-                        listmask[kk] = __reduce_or_sync(kFull, mine);
-                    }
-                }
-                // ---------------- emit pixel x = c - 2r ----------------
-                if (c >= two_r) {
-                    const uint32_t x = c - two_r;
-#pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        if ((uint32_t)(k * 32) + lane < n) {
-                            const float w = __fmul_rn(__uint2float_rn(cnt[k]), inv);
-                            dst[k * 32] = make_uint2(hi[k], __float_as_uint(w));
-                        }
-                    }
-                    dst += n;
-                    if ((x & 31u) == lane) hso_reg = row_first + rowpos;
-                    rowpos += n;
-                    if ((x & 31u) == 31u || x == g.W - 1u) {
-                        if (lane <= (x & 31u)) hso_row[(x & ~31u) + lane] = hso_reg;
-                    }
-                }
-                in_slot = (in_slot + 1u == R) ? 0u : in_slot + 1u;
+                for (int k = 0; k < K; k++) mbuf[lane * K + k] = cmask_row[(size_t)(cb + lane) * K + k];
             }
+            __syncwarp();
+            uint32_t c = cb;
+            while (c < ce) {
+                // a segment: no ring wrap, constant has_out / emit, inside one group of 32 output pixels
+                uint32_t seg_end = min(ce, c + (R - in_slot));
+                const bool has_out = c >= span, emit = c >= two_r;
+                seg_end = has_out ? min(seg_end, c + (R - out_slot)) : min(seg_end, span);
+                seg_end = emit ? min(seg_end, c + 32u - ((c - two_r) & 31u)) : min(seg_end, two_r);
+                const uint8_t* pin = crow + (size_t)in_slot * CS;
+                const uint8_t* pout = crow + (size_t)out_slot * CS;
+                const uint32_t* pm = mbuf + (size_t)(c - cb) * K;
+                uint32_t steps = seg_end - c;
+                uint32_t x = c - two_r;  // only meaningful when emit
+                while (steps > 0u) {
+                    if (steps >= 4u && has_out && emit) {
+                        // ---------------- fast path: four steps without any birth or death ----------------
+                        uint32_t c1[K], c2[K], c3[K], c4[K];
+                        uint32_t bornany = 0u;
+                        bool bad = false;
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            const uint8_t* gi = pin + id[k];
+                            const uint8_t* go = pout + id[k];
+                            c1[k] = cnt[k] + gi[0] - go[0];
+                            c2[k] = c1[k] + gi[CS] - go[CS];
+                            c3[k] = c2[k] + gi[2 * CS] - go[2 * CS];
+                            c4[k] = c3[k] + gi[3 * CS] - go[3 * CS];
+                            bornany |= (pm[k] | pm[K + k] | pm[2 * K + k] | pm[3 * K + k]) & ~listmask[k];
+                            bad |= ((uint32_t)(k * 32) + lane < n) && min(min(c1[k], c2[k]), min(c3[k], c4[k])) == 0u;
+                        }
+                        if (!__any_sync(kFull, bad) && bornany == 0u) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) {
+                                if ((uint32_t)(k * 32) + lane < n) {
+                                    uint2* d = dst + k * 32;
+                                    d[0] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c1[k]), inv)));
+                                    d[n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c2[k]), inv)));
+                                    d[2u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c3[k]), inv)));
+                                    d[3u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c4[k]), inv)));
+                                }
+                                cnt[k] = c4[k];
+                            }
+                            const uint32_t t = (lane - x) & 31u;
+                            if (t < 4u) hso_reg = row_first + rowpos + t * n;
+                            dst += 4u * n;
+                            rowpos += 4u * n;
+                            x += 4u;
+                            if ((x & 31u) == 0u || x == g.W) {
+                                if (lane <= ((x - 1u) & 31u)) hso_row[((x - 1u) & ~31u) + lane] = hso_reg;
+                            }
+                            steps -= 4u;
+                            pin += 4 * CS;
+                            pout += 4 * CS;
+                            pm += 4 * K;
+                            continue;
+                        }
+                    }
+                    // ---------------- one step, any case ----------------
+                    {
+                        bool deadp = false;
+                        uint32_t bornany = 0u;
+                        uint32_t born[K];
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            uint32_t v = cnt[k] + pin[id[k]];
+                            if (has_out) v -= pout[id[k]];
+                            cnt[k] = v;
+                            born[k] = pm[k] & ~listmask[k];
+                            bornany |= born[k];
+                            deadp |= ((uint32_t)(k * 32) + lane < n) && v == 0u;
+                        }
+                        if (__any_sync(kFull, deadp) || bornany != 0u) {
+                            const uint32_t c_now = seg_end - steps;
+                            // (1) drop dead bins, keeping the order of the survivors (SHF.cpp:435-445)
+                            {
+                                uint32_t keep_base = 0u;
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    const bool alive = ((uint32_t)(k * 32) + lane < n) && cnt[k] != 0u;
+                                    const unsigned am = __ballot_sync(kFull, alive);
+                                    if (alive) {
+                                        const uint32_t idx = keep_base + __popc(am & lanemask_lt());
+                                        sA[idx] = (hi[k] << 16) | id[k];
+                                        sB[idx] = cnt[k];
+                                    }
+                                    keep_base += __popc(am);
+                                }
+                                __syncwarp();
+                                if (keep_base != n) {
+                                    n = keep_base;
+#pragma unroll
+                                    for (int k = 0; k < K; k++) {
+                                        const uint32_t e = k * 32 + lane;
+                                        if (e < n) {
+                                            const uint32_t packed = sA[e];
+                                            id[k] = packed & 0xFFFFu;
+                                            hi[k] = packed >> 16;
+                                            cnt[k] = sB[e];
+                                        }
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            // (2) append the bins born in this column, ordered by their vertical chain start
+                            //     (SHF.cpp:411-415: the column's own bin order is the horizontal pass's insertion order)
+                            uint32_t nb = 0u;
+#pragma unroll
+                            for (int k = 0; k < K; k++) nb += __popc(born[k]);
+                            if (nb) {
+                                uint32_t pending[K];
+#pragma unroll
+                                for (int k = 0; k < K; k++) pending[k] = born[k];
+                                uint32_t found = 0u;
+                                // walk the window rows of the column bottom-up, 32 rows at a time: the lowest occurrence
+                                // of a biome carries its chain start in vstart
+                                for (uint32_t blk = 0u; blk * 32u < span && found < nb; blk++) {
+                                    const int32_t off = (int32_t)two_r - (int32_t)(blk * 32u + lane);
+                                    const bool valid = off >= 0;
+                                    const size_t at = (size_t)(y + (valid ? off : 0)) * g.P + c_now;
+                                    const uint32_t sv = valid ? (uint32_t)cm[at] : 0xFFFFu;
+                                    const bool inpend = valid && test_bit<K>(pending, sv);
+                                    const unsigned same = __match_any_sync(kFull, sv);
+                                    const bool first = inpend && ((uint32_t)(__ffs(same) - 1) == lane);
+                                    const unsigned fm = __ballot_sync(kFull, first);
+                                    if (first) {
+                                        const uint32_t idx = found + __popc(fm & lanemask_lt());
+                                        sA[idx] = ((uint32_t)sdict[sv] << 16) | sv;
+                                        sB[idx] = ((uint32_t)vs[at] << 16) | (uint32_t)pin[sv];
+                                    }
+                                    found += __popc(fm);
+#pragma unroll
+                                    for (int k = 0; k < K; k++) {
+                                        const uint32_t mine = (first && (sv >> 5) == (uint32_t)k) ? (1u << (sv & 31u)) : 0u;
+                                        pending[k] &= ~__reduce_or_sync(kFull, mine);
+                                    }
+                                }
+                                __syncwarp();
+                                // rank by chain start row (unique per biome within a column)
+                                uint32_t ra[K], rb[K], rank[K];
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    const uint32_t idx = k * 32 + lane;
+                                    rank[k] = idx;
+                                    ra[k] = 0u;
+                                    rb[k] = 0u;
+                                    if (idx < nb) {
+                                        ra[k] = sA[idx];
+                                        rb[k] = sB[idx];
+                                        uint32_t rk = 0u;
+                                        for (uint32_t i = 0u; i < nb; i++) rk += (sB[i] >> 16) < (rb[k] >> 16);
+                                        rank[k] = rk;
+                                    }
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    if ((uint32_t)(k * 32) + lane < nb) {
+                                        sA[rank[k]] = ra[k];
+                                        sB[rank[k]] = rb[k];
+                                    }
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    const uint32_t e = k * 32 + lane;
+                                    if (e >= n && e < n + nb) {
+                                        const uint32_t packed = sA[e - n];
+                                        id[k] = packed & 0xFFFFu;
+                                        hi[k] = packed >> 16;
+                                        cnt[k] = sB[e - n] & 0xFFFFu;
+                                    }
+                                }
+                                n += nb;
+                                __syncwarp();
+                            }
+                            // (3) membership mask of the list
+#pragma unroll
+                            for (int kk = 0; kk < K; kk++) {
+                                uint32_t mine = 0u;
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    if ((uint32_t)(k * 32) + lane < n && (id[k] >> 5) == (uint32_t)kk)
+                                        mine |= 1u << (id[k] & 31u);
+                                }
+                                listmask[kk] = __reduce_or_sync(kFull, mine);
+                            }
+                        }
+                        if (emit) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) {
+                                if ((uint32_t)(k * 32) + lane < n)
+                                    dst[k * 32] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(cnt[k]), inv)));
+                            }
+                            if ((x & 31u) == lane) hso_reg = row_first + rowpos;
+                            dst += n;
+                            rowpos += n;
+                            x += 1u;
+                            if ((x & 31u) == 0u || x == g.W) {
+                                if (lane <= ((x - 1u) & 31u)) hso_row[((x - 1u) & ~31u) + lane] = hso_reg;
+                            }
+                        }
+                        steps -= 1u;
+                        pin += CS;
+                        pout += CS;
+                        pm += K;
+                    }
+                }
+                const uint32_t adv = seg_end - c;
+                in_slot += adv;
+                if (in_slot >= R) in_slot -= R;
+                out_slot += adv;
+                if (out_slot >= R) out_slot -= R;
+                c = seg_end;
+            }
+        } else {
+            const uint32_t adv = ce - cb;
+            in_slot += adv;
+            if (in_slot >= R) in_slot -= R;
+            out_slot += adv;
+            if (out_slot >= R) out_slot -= R;
         }
-        slot0 += kBatchCols;
-        if (slot0 >= R) slot0 -= R;
+        if (b + stages < n_batches) named_bar_arrive(1u + stages + s, all_threads);  // EMPTY(s)
     }
 }
 

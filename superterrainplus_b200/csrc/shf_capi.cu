@@ -162,7 +162,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     } else {
         const size_t smem = march_smem(g.TY, g.R, K);
         SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + 1) * 32, smem, s>>>(
+        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
             g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
             b->dict.as<uint16_t>(), 32 * K, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(),
             b->hso.as<uint32_t>());
@@ -247,6 +247,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     g.K = K;
     g.Bpad = 32u * K;
     g.stages = 3u;
+    g.producers = 2u;
     g.R = g.span + shf::kMarchNB * g.stages;
     g.VS = g.Bpad;
     // rows per CTA: as many as fit the shared memory, at most 16 (and at most H)
@@ -254,6 +255,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
     if (smem_of(ty) > f->smem_optin) {  // prefer two look-ahead batches over fewer rows per CTA
         g.stages = 2u;
+        g.producers = 1u;
         g.R = g.span + shf::kMarchNB * g.stages;
     }
     while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;

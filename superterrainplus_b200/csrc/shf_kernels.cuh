@@ -38,7 +38,8 @@ struct Geo {
     uint32_t TY, T;                // rows per march CTA, tiles per chunk
     uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
     uint32_t R;                    // ring columns = span + 16 * stages
-    uint32_t stages;               // batches the march producer may run ahead (2 or 3)
+    uint32_t stages;               // batches the march producers may run ahead of the consumers (2 or 3)
+    uint32_t producers;            // producer warps of the march kernel (1 or 2; 2 needs 3 stages)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
 };
@@ -292,7 +293,7 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) 
 constexpr int kMarchNB = 16;
 
 template <int K>
-__global__ void __launch_bounds__(544, 1)
+__global__ void __launch_bounds__(576, 1)
     march_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint16_t* __restrict__ vstart,
                  const uint8_t* __restrict__ base, const uint32_t* __restrict__ colmask,
                  const uint16_t* __restrict__ dict, uint32_t dict_stride, const uint32_t* __restrict__ rowbase,
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(544, 1)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
     const uint32_t y0 = tile * TY;
-    const uint32_t all_threads = (TY + 1u) * 32u;
+    const uint32_t NP = g.producers;                  // producer warps; producer p owns batches b = p (mod NP)
+    const uint32_t bar_threads = (TY + 1u) * 32u;     // every hand-over: all consumer warps + the batch's producer
     const uint32_t n_batches = (PW + NB - 1u) / NB;
 
     uint8_t* cring = smem;
@@ -317,16 +319,16 @@ __global__ void __launch_bounds__(544, 1)
     __syncthreads();
     const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
 
-    if (warp == TY) {
-        // =============================== producer warp ===============================
+    if (warp >= TY) {
+        // =============================== producer warps ===============================
         constexpr int LPC = 2 * K;       // lanes per column, 16 bytes each
         constexpr int CPP = 32 / LPC;    // columns per pass
         const uint32_t part = lane % LPC, colq = lane / LPC;
         const uint32_t tile_rows = min(TY, g.H - y0);
-        uint32_t slot0 = 0u;  // ring slot of the batch's first column
-        for (uint32_t b = 0u; b < n_batches; b++) {
+        for (uint32_t b = warp - TY; b < n_batches; b += NP) {
             const uint32_t s = b % stages, cb = b * NB;
-            if (b >= stages) named_bar_sync(1u + stages + s, all_threads);  // EMPTY(s): batch b - stages is consumed
+            const uint32_t slot0 = cb % R;  // ring slot of the batch's first column
+            if (b >= stages) named_bar_sync(1u + stages + s, bar_threads);  // EMPTY(s): batch b - stages is consumed
 #pragma unroll 1
             for (uint32_t pass = 0u; pass < (uint32_t)(NB / CPP); pass++) {
                 const uint32_t cu = pass * CPP + colq;
@@ -359,9 +361,7 @@ __global__ void __launch_bounds__(544, 1)
                 }
             }
             __threadfence_block();
-            named_bar_arrive(1u + s, all_threads);  // FULL(s)
-            slot0 += NB;
-            if (slot0 >= R) slot0 -= R;
+            named_bar_arrive(1u + s, bar_threads);  // FULL(s)
         }
         return;
     }
@@ -392,16 +392,24 @@ __global__ void __launch_bounds__(544, 1)
     uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
     const float inv = g.inv_total;
 
+    // presence masks of the next batch, one column per lane, fetched a batch ahead
+    uint32_t mnext[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) mnext[k] = (row_active && lane < (uint32_t)NB && lane < PW) ? cmask_row[(size_t)lane * K + k] : 0u;
+
     uint32_t in_slot = 0u;                       // ring slot of column c
     uint32_t out_slot = (R - span % R) % R;      // ring slot of column c - span (meaningful once c >= span)
     for (uint32_t b = 0u; b < n_batches; b++) {
         const uint32_t s = b % stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
-        named_bar_sync(1u + s, all_threads);  // FULL(s)
+        named_bar_sync(1u + s, bar_threads);  // FULL(s)
         if (row_active) {
-            if (lane < (uint32_t)NB && cb + lane < PW) {
+            if (lane < (uint32_t)NB) {
 #pragma unroll
-                for (int k = 0; k < K; k++) mbuf[lane * K + k] = cmask_row[(size_t)(cb + lane) * K + k];
+                for (int k = 0; k < K; k++) mbuf[lane * K + k] = mnext[k];
+                const uint32_t cn = cb + NB + lane;
+#pragma unroll
+                for (int k = 0; k < K; k++) mnext[k] = cn < PW ? cmask_row[(size_t)cn * K + k] : 0u;
             }
             __syncwarp();
             uint32_t c = cb;
@@ -452,6 +460,24 @@ __global__ void __launch_bounds__(544, 1)
                             x += 4u;
                             if ((x & 31u) == 0u || x == g.W) {
                                 if (lane <= ((x - 1u) & 31u)) hso_row[((x - 1u) & ~31u) + lane] = hso_reg;
+                            }
+                            steps -= 4u;
+                            pin += 4 * CS;
+                            pout += 4 * CS;
+                            pm += 4 * K;
+                            continue;
+                        }
+                    } else if (steps >= 4u && !has_out && !emit) {
+                        // ---------------- fast path while the window fills: counts only grow, no pixel yet ----------------
+                        uint32_t bornany = 0u;
+#pragma unroll
+                        for (int k = 0; k < K; k++)
+                            bornany |= (pm[k] | pm[K + k] | pm[2 * K + k] | pm[3 * K + k]) & ~listmask[k];
+                        if (bornany == 0u) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) {
+                                const uint8_t* gi = pin + id[k];
+                                cnt[k] += (uint32_t)gi[0] + gi[CS] + gi[2 * CS] + gi[3 * CS];
                             }
                             steps -= 4u;
                             pin += 4 * CS;
@@ -625,7 +651,7 @@ __global__ void __launch_bounds__(544, 1)
             out_slot += adv;
             if (out_slot >= R) out_slot -= R;
         }
-        if (b + stages < n_batches) named_bar_arrive(1u + stages + s, all_threads);  // EMPTY(s)
+        if (b + stages < n_batches) named_bar_arrive(1u + stages + s, bar_threads);  // EMPTY(s)
     }
 }
 

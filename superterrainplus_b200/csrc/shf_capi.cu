@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <string>
@@ -150,7 +151,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         SHF_CUDA(b->mark(2, s));
         // one warp per row; shrink the CTA until its two mask rows per warp fit
         uint32_t warps = 4;
-        const size_t per_warp = (size_t)2 * g.PW * K * 4;
+        const size_t per_warp = (size_t)3 * g.PW * K * 4;
         while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
         if (per_warp > 200 * 1024) return fail(SHF_ERR_UNSUPPORTED, "row masks fit shared memory", "map too wide");
         SHF_CUDA(cudaFuncSetAttribute(shf::rowcount_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -228,7 +229,12 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(b->mark(0, s));
     SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
     const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), n_chunks);
-    shf::presence_kernel<<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
+    // 16-byte loads when the halo view allows it
+    const bool vec8 = (reinterpret_cast<uintptr_t>(in_dev) % 16u == 0u) && (in_row_stride % 8u == 0u) && (in_chunk_stride % 8u == 0u);
+    if (vec8)
+        shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
+    else
+        shf::presence_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
     tls_launches++;
     shf::dict_prefix_kernel<<<n_chunks, 256, 0, s>>>(b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
                                                      b->nbiomes.as<uint32_t>());
@@ -280,8 +286,12 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     const size_t n_off = (size_t)n_chunks * ((size_t)W * H + 1u);
     SHF_CUDA(b->hso.ensure(n_off * 4));
 
-    shf::remap_kernel<<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
-                                            b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
+    if (vec8)
+        shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
+    else
+        shf::remap_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
 

@@ -47,18 +47,34 @@ struct Geo {
 // ------------------------------------------------------------------------------------------------------------------
 // dictionary
 // ------------------------------------------------------------------------------------------------------------------
+// V = samples per load: 8 (one 16-byte load; needs a 16-byte aligned view and row stride) or 1
+template <int V>
 __global__ void presence_kernel(const uint16_t* __restrict__ in, Geo g, uint32_t* __restrict__ bitmap) {
     __shared__ uint32_t bm[kDictWords];
     const uint32_t n = blockIdx.y;
     for (int i = threadIdx.x; i < kDictWords; i += blockDim.x) bm[i] = 0u;
     __syncthreads();
     const uint16_t* src = in + (size_t)n * g.in_chunk_stride;
+    auto mark = [&](uint32_t s) {
+        const uint32_t bit = 1u << (s & 31u);
+        if (!(((volatile uint32_t*)bm)[s >> 5] & bit)) atomicOr(&bm[s >> 5], bit);
+    };
     for (uint32_t p = blockIdx.x; p < g.PH; p += gridDim.x) {
         const uint16_t* row = src + (size_t)p * g.in_row_stride;
-        for (uint32_t c = threadIdx.x; c < g.PW; c += blockDim.x) {
-            const uint32_t s = row[c];
-            const uint32_t bit = 1u << (s & 31u);
-            if (!(((volatile uint32_t*)bm)[s >> 5] & bit)) atomicOr(&bm[s >> 5], bit);
+        if (V == 8) {
+            const uint32_t nv = g.PW / 8u;
+            for (uint32_t v = threadIdx.x; v < nv; v += blockDim.x) {
+                const uint4 q = reinterpret_cast<const uint4*>(row)[v];
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    mark(w[t] & 0xFFFFu);
+                    if ((w[t] >> 16) != (w[t] & 0xFFFFu)) mark(w[t] >> 16);
+                }
+            }
+            for (uint32_t c = nv * 8u + threadIdx.x; c < g.PW; c += blockDim.x) mark(row[c]);
+        } else {
+            for (uint32_t c = threadIdx.x; c < g.PW; c += blockDim.x) mark(row[c]);
         }
     }
     __syncthreads();
@@ -94,6 +110,7 @@ __global__ void dict_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t
 }
 
 // remap samples to compact ids; CTA x==0 of every chunk also writes the dictionary (compact id -> sample value)
+template <int V>
 __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint32_t* __restrict__ bitmap,
                              const uint32_t* __restrict__ prefix, uint16_t* __restrict__ cmap,
                              uint16_t* __restrict__ dict, uint32_t dict_stride) {
@@ -105,13 +122,25 @@ __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint3
         pf[i] = prefix[(size_t)n * kDictWords + i];
     }
     __syncthreads();
+    auto rank = [&](uint32_t s) { return pf[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31u)) - 1u)); };
     const uint16_t* src = in + (size_t)n * g.in_chunk_stride;
     for (uint32_t p = blockIdx.x; p < g.PH; p += gridDim.x) {
         const uint16_t* row = src + (size_t)p * g.in_row_stride;
         uint16_t* dst = cmap + ((size_t)n * g.PH + p) * g.P;
-        for (uint32_t c = threadIdx.x; c < g.PW; c += blockDim.x) {
-            const uint32_t s = row[c];
-            dst[c] = (uint16_t)(pf[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31u)) - 1u)));
+        if (V == 8) {
+            const uint32_t nv = g.PW / 8u;
+            for (uint32_t v = threadIdx.x; v < nv; v += blockDim.x) {
+                const uint4 q = reinterpret_cast<const uint4*>(row)[v];
+                uint4 o;
+                o.x = rank(q.x & 0xFFFFu) | (rank(q.x >> 16) << 16);
+                o.y = rank(q.y & 0xFFFFu) | (rank(q.y >> 16) << 16);
+                o.z = rank(q.z & 0xFFFFu) | (rank(q.z >> 16) << 16);
+                o.w = rank(q.w & 0xFFFFu) | (rank(q.w >> 16) << 16);
+                reinterpret_cast<uint4*>(dst)[v] = o;
+            }
+            for (uint32_t c = nv * 8u + threadIdx.x; c < g.PW; c += blockDim.x) dst[c] = (uint16_t)rank(row[c]);
+        } else {
+            for (uint32_t c = threadIdx.x; c < g.PW; c += blockDim.x) dst[c] = (uint16_t)rank(row[c]);
         }
     }
     if (blockIdx.x == 0) {
@@ -160,37 +189,51 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     uint32_t* mcol = colmask + ((size_t)n * g.H * g.PW + c) * K;
     const uint32_t span = g.span, two_r = 2u * g.r;
     uint32_t next_tile_row = 0u, tile = 0u;
-    for (uint32_t p = 0; p < g.PH; p++) {
-        const uint32_t s = col[(size_t)p * g.P];
-        const uint32_t l = last[s];
-        if (l == kNoRow || p - l > span) start[s] = (uint16_t)p;
-        last[s] = (uint16_t)p;
-        vcol[(size_t)p * g.P] = start[s];
-        if (++hist[s] == 1) {
+    for (uint32_t p0 = 0; p0 < g.PH; p0 += 8u) {
+        // the loads of 8 rows go out together; the per-row work below is a chain of shared-memory updates
+        uint32_t s_in[8], s_out[8];
 #pragma unroll
-            for (int k = 0; k < K; k++)
-                if ((s >> 5) == (uint32_t)k) mask[k] |= 1u << (s & 31u);
+        for (int j = 0; j < 8; j++) {
+            const uint32_t p = p0 + j;
+            s_in[j] = p < g.PH ? (uint32_t)col[(size_t)p * g.P] : 0u;
+            s_out[j] = (p < g.PH && p >= span) ? (uint32_t)col[(size_t)(p - span) * g.P] : 0u;
         }
-        if (p >= span) {
-            const uint32_t o = col[(size_t)(p - span) * g.P];
-            if (--hist[o] == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t p = p0 + j;
+            if (p >= g.PH) break;
+            const uint32_t s = s_in[j];
+            const uint32_t l = last[s];
+            if (l == kNoRow || p - l > span) start[s] = (uint16_t)p;
+            last[s] = (uint16_t)p;
+            vcol[(size_t)p * g.P] = start[s];
+            if (++hist[s] == 1) {
 #pragma unroll
                 for (int k = 0; k < K; k++)
-                    if ((o >> 5) == (uint32_t)k) mask[k] &= ~(1u << (o & 31u));
+                    if ((s >> 5) == (uint32_t)k) mask[k] |= 1u << (s & 31u);
             }
-        }
-        if (p >= two_r) {
-            const uint32_t y = p - two_r;  // the window [y, y+2r] is complete
+            if (p >= span) {
+                const uint32_t o = s_out[j];
+                if (--hist[o] == 0) {
 #pragma unroll
-            for (int k = 0; k < K; k++) mcol[(size_t)y * g.PW * K + k] = mask[k];
-            if (y == next_tile_row) {
-                const size_t slot = ((size_t)n * g.T + tile) * g.PW + c;
-                uint4* dst = reinterpret_cast<uint4*>(base + slot * Bpad);
-                const uint32_t* hw = reinterpret_cast<const uint32_t*>(hist);
+                    for (int k = 0; k < K; k++)
+                        if ((o >> 5) == (uint32_t)k) mask[k] &= ~(1u << (o & 31u));
+                }
+            }
+            if (p >= two_r) {
+                const uint32_t y = p - two_r;  // the window [y, y+2r] is complete
 #pragma unroll
-                for (int q = 0; q < 2 * K; q++) dst[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-                tile++;
-                next_tile_row += g.TY;
+                for (int k = 0; k < K; k++) mcol[(size_t)y * g.PW * K + k] = mask[k];
+                if (y == next_tile_row) {
+                    const size_t slot = ((size_t)n * g.T + tile) * g.PW + c;
+                    uint4* dst = reinterpret_cast<uint4*>(base + slot * Bpad);
+                    const uint32_t* hw = reinterpret_cast<const uint32_t*>(hist);
+#pragma unroll
+                    for (int q = 0; q < 2 * K; q++)
+                        dst[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+                    tile++;
+                    next_tile_row += g.TY;
+                }
             }
         }
     }
@@ -208,44 +251,33 @@ __global__ void __launch_bounds__(128) rowcount_kernel(Geo g, const uint32_t* __
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t y = blockIdx.x * (blockDim.x >> 5) + warp, n = blockIdx.y;
     if (y >= g.H) return;
-    const uint32_t PW = g.PW;
-    uint32_t* powr = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 2 * PW * K;  // window of length 2^k at i
-    uint32_t* acc = powr + (size_t)PW * K;                                          // window of length L at i
-    const uint32_t* src = colmask + ((size_t)n * g.H + y) * PW * K;
-    for (uint32_t i = lane; i < PW * K; i += 32u) {
-        powr[i] = src[i];
+    const uint32_t PW = g.PW, NW = PW * K;  // a row of masks as NW words, mask i = words [i*K, i*K+K)
+    uint32_t* pa = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 3 * NW;  // window of length 2^k at i (ping)
+    uint32_t* pb = pa + NW;                                                    // (pong)
+    uint32_t* acc = pb + NW;                                                   // window of length L at i
+    const uint32_t* src = colmask + ((size_t)n * g.H + y) * NW;
+    for (uint32_t i = lane; i < NW; i += 32u) {
+        pa[i] = src[i];
         acc[i] = 0u;
     }
     __syncwarp();
     uint32_t L = 0u;
     for (uint32_t bit = 1u; bit <= g.span; bit <<= 1) {
         if (g.span & bit) {  // acc(i) |= pow(i + L): extends every window from length L to L + bit
-            for (uint32_t i = lane; i + L < PW; i += 32u)
-#pragma unroll
-                for (int k = 0; k < K; k++) acc[i * K + k] |= powr[(i + L) * K + k];
+            for (uint32_t i = lane; i + L * K < NW; i += 32u) acc[i] |= pa[i + L * K];
             L += bit;
-            __syncwarp();
         }
-        if ((bit << 1) <= g.span) {  // pow(i) |= pow(i + bit), in place: read everything first, then write
-            uint32_t tmp[K];
-            for (uint32_t i0 = 0u; i0 + bit < PW; i0 += 32u) {
-                const uint32_t i = i0 + lane;
-                const bool ok = i + bit < PW;
-#pragma unroll
-                for (int k = 0; k < K; k++) tmp[k] = ok ? powr[(i + bit) * K + k] : 0u;
-                __syncwarp();
-                if (ok) {
-#pragma unroll
-                    for (int k = 0; k < K; k++) powr[i * K + k] |= tmp[k];
-                }
-                __syncwarp();
-            }
+        if ((bit << 1) <= g.span) {  // pow'(i) = pow(i) | pow(i + bit)
+            const uint32_t sh = bit * K;
+            for (uint32_t i = lane; i < NW; i += 32u) pb[i] = pa[i] | (i + sh < NW ? pa[i + sh] : 0u);
+            uint32_t* t = pa;
+            pa = pb;
+            pb = t;
         }
+        __syncwarp();
     }
     uint32_t total = 0u;
-    for (uint32_t x = lane; x < g.W; x += 32u)
-#pragma unroll
-        for (int k = 0; k < K; k++) total += __popc(acc[x * K + k]);
+    for (uint32_t i = lane; i < g.W * K; i += 32u) total += __popc(acc[i]);
     total = __reduce_add_sync(kFull, total);
     if (lane == 0u) rowtotal[(size_t)n * g.H + y] = total;
 }

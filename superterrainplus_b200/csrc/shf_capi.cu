@@ -134,7 +134,7 @@ namespace {
 using shf::Geo;
 
 size_t march_smem(uint32_t ty, uint32_t R, int K) {
-    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2;
+    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2 + 128;
 }
 
 // phase 0: vertical scan + bins per row; phase 1: the emitting march
@@ -252,18 +252,21 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
     g.K = K;
     g.Bpad = 32u * K;
-    g.stages = 3u;
-    g.producers = 2u;
-    g.R = g.span + shf::kMarchNB * g.stages;
-    g.VS = g.Bpad;
-    // rows per CTA: as many as fit the shared memory, at most 16 (and at most H)
+    // march kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
+    // `ppb` passes; with `np` producer warps ceil(np / ppb) batches are in production at once, and the ring must hold
+    // one more batch than that besides the 2r+1 columns the consumers still read.
+    const uint32_t ppb = K == 1 ? 1u : K == 2 ? 2u : K == 4 ? 4u : 8u;
     uint32_t ty = std::min<uint32_t>(16u, H);
-    auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
-    if (smem_of(ty) > f->smem_optin) {  // prefer two look-ahead batches over fewer rows per CTA
-        g.stages = 2u;
-        g.producers = 1u;
+    auto plan = [&](uint32_t np, uint32_t extra) {
+        g.producers = np;
+        g.stages = (np + ppb - 1u) / ppb + extra;
         g.R = g.span + shf::kMarchNB * g.stages;
-    }
+    };
+    auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
+    plan(4u, 2u);
+    if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
+    if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
+    if (smem_of(ty) > f->smem_optin) plan(1u, 1u);
     while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
     if (smem_of(ty) > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "ring fits shared memory", "radius x biome count too large for one CTA");

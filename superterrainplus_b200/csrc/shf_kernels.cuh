@@ -38,8 +38,8 @@ struct Geo {
     uint32_t TY, T;                // rows per march CTA, tiles per chunk
     uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
     uint32_t R;                    // ring columns = span + 16 * stages
-    uint32_t stages;               // batches the march producers may run ahead of the consumers (2 or 3)
-    uint32_t producers;            // producer warps of the march kernel (1 or 2; 2 needs 3 stages)
+    uint32_t stages;               // batches the march producers may run ahead of the consumers (2..6)
+    uint32_t producers;            // producer warps of the march kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
 };
@@ -300,11 +300,30 @@ __device__ __forceinline__ bool test_bit(const uint32_t (&words)[K], uint32_t s)
     return hit;
 }
 
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+// shared-memory mbarriers (arrive = release, wait = acquire at CTA scope): the producer -> consumer hand-over must not
+// make the consumer warps wait for each other, which a bar.sync would
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// PTX shl clamps shift amounts above 31 to 32, i.e. the result is 0 (C++ leaves such shifts undefined)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t sh) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 
 // Shared memory of a march CTA (TY consumer warps = TY rows, plus one producer warp):
@@ -315,8 +334,8 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) 
 // The producer warp runs `stages` batches of NB = 16 columns ahead of the consumers. For a column it keeps the count
 // vector in registers (2K lanes x 16 bytes), starts from the tile's base vector, and walks down the tile's rows: store
 // the row's slot (one 128-bit store per lane, neighbouring columns fill one 128-byte line), then apply the one sample
-// entering and the one leaving the vertical window. Hand-over uses named barriers: FULL(s) producer -> consumers,
-// EMPTY(s) consumers -> producer, s = batch % stages.
+// entering and the one leaving the vertical window. Hand-over uses mbarriers: full[s] producer -> consumers (count 1),
+// empty[s] consumers -> producers (count TY), s = batch % stages; a consumer warp never waits for another consumer.
 //
 // A consumer warp keeps its row's ordered bin list in registers: entry e = k*32 + lane (valid iff e < n) is the triple
 // id (compact id) / hi (sample value) / cnt (window count). A step adds column c, removes column c - (2r+1), handles
@@ -325,7 +344,7 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) 
 constexpr int kMarchNB = 16;
 
 template <int K>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(640, 1)
     march_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint16_t* __restrict__ vstart,
                  const uint8_t* __restrict__ base, const uint32_t* __restrict__ colmask,
                  const uint16_t* __restrict__ dict, uint32_t dict_stride, const uint32_t* __restrict__ rowbase,
@@ -339,61 +358,69 @@ __global__ void __launch_bounds__(576, 1)
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
     const uint32_t y0 = tile * TY;
     const uint32_t NP = g.producers;                  // producer warps; producer p owns batches b = p (mod NP)
-    const uint32_t bar_threads = (TY + 1u) * 32u;     // every hand-over: all consumer warps + the batch's producer
     const uint32_t n_batches = (PW + NB - 1u) / NB;
 
     uint8_t* cring = smem;
     uint32_t* mbuf_all = reinterpret_cast<uint32_t*>(smem + (size_t)TY * R * CS);
     uint32_t* scratch = mbuf_all + (size_t)TY * NB * K;
     uint16_t* sdict = reinterpret_cast<uint16_t*>(scratch + (size_t)TY * 2 * E);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sdict + E);  // [stages]
+    uint64_t* empty_bar = full_bar + 8;                            // [stages]
     for (uint32_t i = threadIdx.x; i < (uint32_t)E; i += blockDim.x)
         sdict[i] = (i < dict_stride) ? dict[(size_t)n_chunk * dict_stride + i] : (uint16_t)0;
+    if (threadIdx.x < stages) {
+        mbar_init(&full_bar[threadIdx.x], (uint32_t)(NB / (32 / (2 * K))));  // one arrival per pass of the batch
+        mbar_init(&empty_bar[threadIdx.x], TY);
+    }
     __syncthreads();
     const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
 
     if (warp >= TY) {
         // =============================== producer warps ===============================
+        // work item t = (batch b, pass q), t = b * PPB + q; producer p owns the items t = p (mod NP)
         constexpr int LPC = 2 * K;       // lanes per column, 16 bytes each
         constexpr int CPP = 32 / LPC;    // columns per pass
+        constexpr int PPB = NB / CPP;    // passes per batch
         const uint32_t part = lane % LPC, colq = lane / LPC;
         const uint32_t tile_rows = min(TY, g.H - y0);
-        for (uint32_t b = warp - TY; b < n_batches; b += NP) {
+        const uint32_t bit0 = part * 128u;  // bit position of my first counter inside the column's count vector
+        for (uint32_t t = warp - TY; t < n_batches * PPB; t += NP) {
+            const uint32_t b = t / PPB, pass = t % PPB;
             const uint32_t s = b % stages, cb = b * NB;
             const uint32_t slot0 = cb % R;  // ring slot of the batch's first column
-            if (b >= stages) named_bar_sync(1u + stages + s, bar_threads);  // EMPTY(s): batch b - stages is consumed
-#pragma unroll 1
-            for (uint32_t pass = 0u; pass < (uint32_t)(NB / CPP); pass++) {
-                const uint32_t cu = pass * CPP + colq;
-                const bool live = cb + cu < PW;
-                const uint32_t c = live ? cb + cu : PW - 1u;
-                uint32_t slot = slot0 + cu;
-                if (slot >= R) slot -= R;
-                uint4 v = *reinterpret_cast<const uint4*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS + part * 16u);
-                // samples entering / leaving the vertical window when it moves from tile row i to i+1
-                uint32_t sa[16], so[16];
+            const uint32_t cu = pass * CPP + colq;
+            const bool live = cb + cu < PW;
+            const uint32_t c = live ? cb + cu : PW - 1u;
+            uint32_t slot = slot0 + cu;
+            if (slot >= R) slot -= R;
+            uint4 v = *reinterpret_cast<const uint4*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS + part * 16u);
+            // samples entering / leaving the vertical window when it moves from tile row i to i+1
+            uint32_t sa[16], so[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
-                    sa[i] = cm[(size_t)pi * g.P + c];
-                    so[i] = cm[(size_t)po * g.P + c];
-                }
-                uint8_t* out = cring + (size_t)slot * CS + part * 16u;
+            for (int i = 0; i < 16; i++) {
+                const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
+                sa[i] = cm[(size_t)pi * g.P + c];
+                so[i] = cm[(size_t)po * g.P + c];
+            }
+            if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);  // batch b - stages is consumed
+            uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if ((uint32_t)i < tile_rows) {
-                        if (live) *reinterpret_cast<uint4*>(out) = v;
-                        out += (size_t)R * CS;
-                        const uint32_t wa = (sa[i] >> 2) - part * 4u, ia = 1u << ((sa[i] & 3u) * 8u);
-                        const uint32_t wo = (so[i] >> 2) - part * 4u, io = 1u << ((so[i] & 3u) * 8u);
-                        v.x += (wa == 0u ? ia : 0u) - (wo == 0u ? io : 0u);
-                        v.y += (wa == 1u ? ia : 0u) - (wo == 1u ? io : 0u);
-                        v.z += (wa == 2u ? ia : 0u) - (wo == 2u ? io : 0u);
-                        v.w += (wa == 3u ? ia : 0u) - (wo == 3u ? io : 0u);
-                    }
+            for (int i = 0; i < 16; i++) {
+                if ((uint32_t)i < tile_rows) {
+                    if (live) *reinterpret_cast<uint4*>(out) = v;
+                    out += (size_t)R * CS;
+                    // counter of compact id a sits at bit 8a of the column vector; a shift by >= 32 (or "negative",
+                    // i.e. huge) yields 0 with PTX shl, so every word only sees its own counters
+                    const uint32_t ba = sa[i] * 8u - bit0, bo = so[i] * 8u - bit0;
+                    v.x += shl_clamp(1u, ba) - shl_clamp(1u, bo);
+                    v.y += shl_clamp(1u, ba - 32u) - shl_clamp(1u, bo - 32u);
+                    v.z += shl_clamp(1u, ba - 64u) - shl_clamp(1u, bo - 64u);
+                    v.w += shl_clamp(1u, ba - 96u) - shl_clamp(1u, bo - 96u);
                 }
             }
             __threadfence_block();
-            named_bar_arrive(1u + s, bar_threads);  // FULL(s)
+            __syncwarp();
+            if (lane == 0u) mbar_arrive(&full_bar[s]);
         }
         return;
     }
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(576, 1)
     for (uint32_t b = 0u; b < n_batches; b++) {
         const uint32_t s = b % stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
-        named_bar_sync(1u + s, bar_threads);  // FULL(s)
+        mbar_wait(&full_bar[s], (b / stages) & 1u);
         if (row_active) {
             if (lane < (uint32_t)NB) {
 #pragma unroll
@@ -683,7 +710,10 @@ __global__ void __launch_bounds__(576, 1)
             out_slot += adv;
             if (out_slot >= R) out_slot -= R;
         }
-        if (b + stages < n_batches) named_bar_arrive(1u + stages + s, bar_threads);  // EMPTY(s)
+        if (b + stages < n_batches) {
+            __syncwarp();
+            if (lane == 0u) mbar_arrive(&empty_bar[s]);
+        }
     }
 }
 

@@ -1,0 +1,121 @@
+// B200-native STPSingleHistogramFilter: the public interface of
+// SuperTerrain+/SuperAlgorithm+/Host/Public/SuperAlgorithm+Host/STPSingleHistogramFilter.h:36-192, with the CPU thread
+// pool and the CPU scratch memory behind it replaced by handles of the CUDA library (include/shf_b200.h).
+//
+// Kept: namespace, class and nested class names, STPExecutionType values, constructors / deleted copies / moves,
+// readHistogram(), size(), type(), operator()(samplemap, nn_info, filter_buffer, radius) and its error behaviour
+// (STPNumericDomainError for a bad radius, STPInvalidEnum for a bad execution type, STPCUDAError for CUDA failures).
+// The sample map is a HOST pointer and the returned histogram lives in PAGE-LOCKED HOST memory owned by the filter
+// buffer, exactly as with the reference, so STPBiomefieldGenerator (SuperDemo+/World/Biomes/STPBiomefieldGenerator.cpp:
+// 102-123) compiles and runs unchanged. Both execution types run the same GPU path.
+//
+// Added (not in the reference): filterBatch(), filterDevice(), readDeviceHistogram(), chunkOffset() for batches of
+// neighbourhoods and for consumers that read the histogram on the device without a host round trip.
+#pragma once
+#ifndef _STP_SINGLE_HISTOGRAM_FILTER_H_
+#define _STP_SINGLE_HISTOGRAM_FILTER_H_
+
+#include <SuperAlgorithm+Host/STPAlgorithmDefine.h>
+#include <SuperTerrain+/World/STPWorldMapPixelFormat.hpp>
+#include <SuperTerrain+/World/Chunk/STPNearestNeighbourInformation.hpp>
+#include "STPSingleHistogram.hpp"
+
+#include <cstddef>
+#include <cstdint>
+#include <utility>
+
+struct shf_filter;
+struct shf_buffer;
+
+namespace SuperTerrainPlus::STPAlgorithm {
+
+	class STP_ALGORITHM_HOST_API STPSingleHistogramFilter {
+	public:
+
+		class STP_ALGORITHM_HOST_API STPFilterBuffer {
+		public:
+
+			enum class STPExecutionType : unsigned char {
+				Serial = 0x00u,
+				Parallel = 0xFFu
+			};
+
+		private:
+
+			friend class STPSingleHistogramFilter;
+
+			//device scratch, device output and page-locked host output of one execution at a time
+			shf_buffer* Memory;
+
+		public:
+
+			//number of bins and number of offsets of the histogram currently held
+			typedef std::pair<size_t, size_t> STPHistogramSize;
+
+			STPFilterBuffer(STPExecutionType);
+
+			STPFilterBuffer(const STPFilterBuffer&) = delete;
+
+			STPFilterBuffer(STPFilterBuffer&&) noexcept;
+
+			STPFilterBuffer& operator=(const STPFilterBuffer&) = delete;
+
+			STPFilterBuffer& operator=(STPFilterBuffer&&) noexcept;
+
+			~STPFilterBuffer();
+
+			//pointers into the buffer's page-locked host memory; {nullptr, nullptr} before the first execution
+			STPSingleHistogram readHistogram() const;
+
+			STPHistogramSize size() const;
+
+			STPExecutionType type() const noexcept;
+
+			/* ---- additive ---- */
+
+			//device pointers of the last result (valid after filterDevice / filterBatch / operator())
+			STPSingleHistogram readDeviceHistogram() const;
+
+			//index of the first bin of chunk `chunk` of the last batch result; chunkOffset(chunk count) = total bins
+			std::uint64_t chunkOffset(unsigned int chunk) const;
+
+		};
+
+	private:
+
+		shf_filter* Filter;
+
+	public:
+
+		STPSingleHistogramFilter();
+
+		STPSingleHistogramFilter(const STPSingleHistogramFilter&) = delete;
+
+		STPSingleHistogramFilter(STPSingleHistogramFilter&&) = delete;
+
+		STPSingleHistogramFilter& operator=(const STPSingleHistogramFilter&) = delete;
+
+		STPSingleHistogramFilter& operator=(STPSingleHistogramFilter&&) = delete;
+
+		~STPSingleHistogramFilter();
+
+		//samplemap: host pointer, row-major, row stride nn_info.TotalMapSize.x, not retained.
+		//Synchronous; the result is also retrievable later with filter_buffer.readHistogram().
+		STPSingleHistogram operator()(const STPSample_t*, const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int);
+
+		/* ---- additive ---- */
+
+		//`chunk_count` independent neighbourhoods of equal geometry, host maps in, page-locked host histograms out:
+		//bins concatenated, offsets as chunk_count blocks of MapSize.x * MapSize.y + 1 entries relative to each chunk.
+		STPSingleHistogram filterBatch(const STPSample_t* const*, unsigned int chunk_count, const STPNearestNeighbourInformation&,
+			STPFilterBuffer&, unsigned int);
+
+		//merged maps already in device memory (chunk i at samplemap_device + i * chunk_stride samples); the result stays
+		//in device memory (readDeviceHistogram). `stream` is a cudaStream_t; the call returns once the work is enqueued.
+		void filterDevice(const STPSample_t* samplemap_device, std::uint64_t chunk_stride, unsigned int chunk_count,
+			const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int radius, void* stream = nullptr);
+
+	};
+
+}
+#endif//_STP_SINGLE_HISTOGRAM_FILTER_H_

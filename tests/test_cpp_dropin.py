@@ -1,0 +1,35 @@
+"""The C++ drop-in class (include/SuperAlgorithm+Host/STPSingleHistogramFilter.h over the C ABI): it compiles with
+g++ everywhere; on a GPU it passes the reference's own test scenario re-expressed in tests/cpp/test_histogram.cpp."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BINARY = os.path.join(HERE, "cpp", "test_histogram")
+
+
+def build():
+    out = subprocess.run(["bash", os.path.join(HERE, "cpp", "build.sh")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_dropin_compiles_and_fails_loudly_without_gpu(shf):
+    import torch
+
+    shf.library()
+    build()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    run = subprocess.run([BINARY], capture_output=True, text=True)
+    assert run.returncode != 0
+    assert "cudaGetDeviceCount" in run.stderr or "CUDA" in run.stderr
+
+
+@pytest.mark.gpu
+def test_reference_scenario_in_cpp(shf):
+    shf.library()
+    build()
+    run = subprocess.run([BINARY], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "all C++ histogram checks passed" in run.stdout

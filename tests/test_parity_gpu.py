@@ -223,3 +223,25 @@ def test_c3_batch_properties_and_sampled_chunks(shf, filt, oracle_mod):
             want = oracle_mod.run_port(maps[i], wl.map_size, wl.nn, wl.radius)
             assert_same((items.copy(), weights.copy(), offs.astype(np.uint32)), want, f"C3 chunk {i}")
     buf.close()
+
+
+@pytest.mark.parametrize("index", range(14))
+def test_against_stored_reference_outputs(shf, filt, index):
+    """CUDA path vs outputs of the reference's own compiled filter, committed in tests/golden/ref_vectors.npz."""
+    import os
+
+    from golden.cases import CASES, make_case
+
+    case = CASES[index]
+    stored = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+    want = (stored[f"items_{index}"], stored[f"weights_{index}"], stored[f"offsets_{index}"])
+    info = shf.STPNearestNeighbourInformation((case["w"], case["h"]), case["nn"],
+                                              (case["w"] * case["nn"][0], case["h"] * case["nn"][1]))
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    if case["b"] > 256 and index == 9:
+        # more than 256 distinct samples in one neighbourhood: the wide-list kernel is not built yet
+        with pytest.raises(shf.STPUnsupportedError):
+            filt(make_case(case), info, buf, case["r"])
+    else:
+        assert_same(split_result(filt(make_case(case), info, buf, case["r"])), want, f"golden case {index}")
+    buf.close()

@@ -2,6 +2,7 @@
 // sequence of the kernels in shf_kernels.cuh. No torch, no CPU compute path: every result comes from the kernels.
 #include "../../include/shf_b200.h"
 #include "shf_kernels.cuh"
+#include "shf_generic.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -95,7 +96,7 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
-        bins, hso;
+        bins, hso, gstate;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
     uint32_t n_chunks = 0;
@@ -119,7 +120,7 @@ struct shf_buffer {
         }
         ev_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
-                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso};
+                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -195,6 +196,111 @@ int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) 
     return SHF_OK;
 }
 
+// scratch every path needs + the compact-id map and the dictionary
+int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
+    const size_t cells = (size_t)g.n_chunks * g.PH * g.P;
+    SHF_CUDA(b->cmap.ensure(cells * 2));
+    SHF_CUDA(b->vstart.ensure(cells * 2));
+    SHF_CUDA(b->dict.ensure((size_t)g.n_chunks * g.Bpad * 2));
+    SHF_CUDA(b->rowtotal.ensure((size_t)g.n_chunks * g.H * 4));
+    SHF_CUDA(b->rowbase.ensure((size_t)g.n_chunks * g.H * 4));
+    SHF_CUDA(b->chunktotal.ensure((size_t)g.n_chunks * 8));
+    SHF_CUDA(b->chunkbase.ensure((size_t)(g.n_chunks + 1) * 8));
+    SHF_CUDA(b->hso.ensure((size_t)g.n_chunks * ((size_t)g.W * g.H + 1u) * 4));
+    const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), g.n_chunks);
+    if (vec8)
+        shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
+    else
+        shf::remap_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    return SHF_OK;
+}
+
+// bins per row -> first bin of every row, chunk totals on the host (u32 overflow check), the bin buffer
+int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s) {
+    const uint32_t n_chunks = g.n_chunks;
+    SHF_CUDA(b->mark(3, s));
+    shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+                                                  b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    SHF_CUDA(b->mark(4, s));
+    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
+    tls_d2h += (size_t)n_chunks * 8;
+    SHF_CUDA(cudaStreamSynchronize(s));
+    b->chunk_base.assign(n_chunks + 1u, 0ull);
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        if (h_totals[i] > 0xFFFFFFFFull)
+            return fail(SHF_ERR_OFFSET_OVERFLOW, "bins per chunk < 2^32",
+                        "HistogramStartOffset is 32 bits wide; this chunk has too many bins");
+        b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
+    }
+    const size_t total = (size_t)b->chunk_base[n_chunks];
+    SHF_CUDA(b->bins.ensure(std::max<size_t>(total, 1) * sizeof(shf_bin)));
+    SHF_CUDA(cudaMemcpyAsync(b->chunkbase.p, b->chunk_base.data(), (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
+    tls_h2d += (size_t)(n_chunks + 1) * 8;
+    return SHF_OK;
+}
+
+int publish(shf_buffer* b, const Geo& g) {
+    b->ev_valid = g_profiling != 0;
+    b->n_chunks = g.n_chunks;
+    b->n_bins = (size_t)b->chunk_base[g.n_chunks];
+    b->n_offsets = (size_t)g.n_chunks * ((size_t)g.W * g.H + 1u);
+    b->has_result = true;
+    b->on_host = false;
+    return SHF_OK;
+}
+
+// The wide path (shf_generic.cuh): any radius, up to kGenericMaxBiomes distinct values.
+int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, uint32_t bmax,
+                uint64_t* h_totals, cudaStream_t s) {
+    const uint32_t nb = g.Bpad;
+    if (bmax > shf::kGenericMaxBiomes)
+        return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 16384",
+                    "too many distinct sample values in one neighbourhood for the per-row shared-memory tables");
+    const size_t smem = shf::march_generic_smem(nb, g.span);
+    if (smem > f->smem_optin)
+        return fail(SHF_ERR_UNSUPPORTED, "per-row tables fit shared memory", "radius x biome count too large for one CTA");
+    b->plan_smem = (uint32_t)smem;
+    int st = prepare_common(b, g, in_dev, vec8, s);
+    if (st != SHF_OK) return st;
+    // vertical chain starts; per-(biome, column) state for a sub-batch of chunks at a time (<= 1 GiB of scratch)
+    const size_t per_chunk = (size_t)nb * g.PW * 4;
+    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(g.n_chunks, (size_t(1) << 30) / per_chunk));
+    SHF_CUDA(b->gstate.ensure(per_chunk * sub));
+    for (uint32_t first = 0; first < g.n_chunks; first += sub) {
+        const uint32_t cnt = std::min(sub, g.n_chunks - first);
+        SHF_CUDA(cudaMemsetAsync(b->gstate.p, 0xFF, per_chunk * cnt, s));
+        shf::vstart_generic_kernel<<<dim3((g.PW + 127u) / 128u, cnt), 128, 0, s>>>(
+            g, first, nb, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->gstate.as<uint32_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    }
+    SHF_CUDA(b->mark(2, s));
+    SHF_CUDA(cudaFuncSetAttribute(shf::march_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SHF_CUDA(cudaFuncSetAttribute(shf::march_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid(g.H, g.n_chunks);
+    shf::march_generic_kernel<false><<<grid, shf::kGenericThreads, smem, s>>>(
+        g, nb, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->dict.as<uint16_t>(), nb, nullptr, nullptr, nullptr,
+        nullptr, b->rowtotal.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    st = size_output(b, g, h_totals, s);
+    if (st != SHF_OK) return st;
+    SHF_CUDA(b->mark(5, s));
+    shf::march_generic_kernel<true><<<grid, shf::kGenericThreads, smem, s>>>(
+        g, nb, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->dict.as<uint16_t>(), nb, b->rowbase.as<uint32_t>(),
+        b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>(), nullptr);
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    SHF_CUDA(b->mark(6, s));
+    return publish(b, g);
+}
+
 // Run the whole kernel sequence. `in_dev` views the halo-extended region of every chunk in device memory.
 int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t in_chunk_stride, uint32_t in_row_stride,
                   uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s) {
@@ -212,11 +318,8 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     g.inv_total = 1.0f / (float)(g.span * g.span);
     if (W == 0u || H == 0u || n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "W*H*n_chunks > 0", "empty input");
     if (n_chunks > 65535u) return fail(SHF_ERR_UNSUPPORTED, "n_chunks <= 65535", "too many chunks in one batch");
-    if (g.span > 255u)
-        return fail(SHF_ERR_UNSUPPORTED, "2*radius+1 <= 255", "radius above 126 needs 16-bit window counters (not built yet)");
     if (g.PH >= 65535u) return fail(SHF_ERR_UNSUPPORTED, "H + 2*radius < 65535", "map too tall for 16-bit row keys");
 
-    const size_t cells = (size_t)n_chunks * g.PH * g.P;
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
@@ -246,94 +349,62 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(cudaStreamSynchronize(s));
     uint32_t bmax = 0;
     for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
-    if (bmax > 256u)
-        return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 256",
-                    "more than 256 distinct biomes in one neighbourhood (wide-list kernel not built yet)");
+    if (bmax > 65535u) return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 65535", "compact ids are 16 bits wide");
+    // The register-list march covers up to 256 distinct values and 8-bit vertical window counts (2r+1 <= 255) as long
+    // as one row's ring fits shared memory; everything else takes the wide path of shf_generic.cuh.
     const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
     g.K = K;
-    g.Bpad = 32u * K;
-    // march kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
-    // `ppb` passes; with `np` producer warps ceil(np / ppb) batches are in production at once, and the ring must hold
-    // one more batch than that besides the 2r+1 columns the consumers still read.
-    const uint32_t ppb = K == 1 ? 1u : K == 2 ? 2u : K == 4 ? 4u : 8u;
-    uint32_t ty = std::min<uint32_t>(16u, H);
-    auto plan = [&](uint32_t np, uint32_t extra) {
-        g.producers = np;
-        g.stages = (np + ppb - 1u) / ppb + extra;
-        g.R = g.span + shf::kMarchNB * g.stages;
-    };
-    auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
-    plan(4u, 2u);
-    if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
-    if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
-    if (smem_of(ty) > f->smem_optin) plan(1u, 1u);
-    while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
-    if (smem_of(ty) > f->smem_optin)
-        return fail(SHF_ERR_UNSUPPORTED, "ring fits shared memory", "radius x biome count too large for one CTA");
-    g.TY = ty;
-    g.T = (H + ty - 1u) / ty;
-    b->plan_k = K;
-    b->plan_ty = ty;
+    g.Bpad = (bmax + 31u) & ~31u;
+    bool generic = bmax > 256u || g.span > 255u;
+    if (!generic) {
+        g.Bpad = 32u * K;
+        // march kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
+        // `ppb` passes; with `np` producer warps ceil(np / ppb) batches are in production at once, and the ring must
+        // hold one more batch than that besides the 2r+1 columns the consumers still read.
+        const uint32_t ppb = K == 1 ? 1u : K == 2 ? 2u : K == 4 ? 4u : 8u;
+        uint32_t ty = std::min<uint32_t>(16u, H);
+        auto plan = [&](uint32_t np, uint32_t extra) {
+            g.producers = np;
+            g.stages = (np + ppb - 1u) / ppb + extra;
+            g.R = g.span + shf::kMarchNB * g.stages;
+        };
+        auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
+        plan(4u, 2u);
+        if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
+        if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
+        if (smem_of(ty) > f->smem_optin) plan(1u, 1u);
+        while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
+        if (smem_of(ty) > f->smem_optin) {
+            generic = true;
+            g.Bpad = (bmax + 31u) & ~31u;
+        } else {
+            g.TY = ty;
+            g.T = (H + ty - 1u) / ty;
+            b->plan_smem = (uint32_t)smem_of(ty);
+        }
+    }
+    b->plan_k = generic ? 0u : (uint32_t)K;
+    b->plan_ty = generic ? 1u : g.TY;
     b->plan_biomes = bmax;
-    b->plan_smem = (uint32_t)smem_of(ty);
+    if (generic) return run_generic(f, b, g, in_dev, vec8, bmax, h_totals, s);
 
-    SHF_CUDA(b->cmap.ensure(cells * 2));
-    SHF_CUDA(b->vstart.ensure(cells * 2));
-    SHF_CUDA(b->dict.ensure((size_t)n_chunks * g.Bpad * 2));
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
     SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * g.PW * K * 4));
-    SHF_CUDA(b->rowtotal.ensure((size_t)n_chunks * H * 4));
-    SHF_CUDA(b->rowbase.ensure((size_t)n_chunks * H * 4));
-    SHF_CUDA(b->chunktotal.ensure((size_t)n_chunks * 8));
-    SHF_CUDA(b->chunkbase.ensure((size_t)(n_chunks + 1) * 8));
-    const size_t n_off = (size_t)n_chunks * ((size_t)W * H + 1u);
-    SHF_CUDA(b->hso.ensure(n_off * 4));
-
-    if (vec8)
-        shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
-                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
-    else
-        shf::remap_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
-                                                   b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
-    tls_launches++;
-    SHF_CUDA(cudaGetLastError());
-
-    // ---- vertical scan + counting march ----
-    int st = dispatch_chain(K, b, g, s, 0);
+    int st = prepare_common(b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
-    SHF_CUDA(b->mark(3, s));
-    shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
-                                                  b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
-    tls_launches++;
-    SHF_CUDA(cudaGetLastError());
-    SHF_CUDA(b->mark(4, s));
-    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
-    tls_d2h += (size_t)n_chunks * 8;
-    SHF_CUDA(cudaStreamSynchronize(s));
-    b->chunk_base.assign(n_chunks + 1u, 0ull);
-    for (uint32_t i = 0; i < n_chunks; i++) {
-        if (h_totals[i] > 0xFFFFFFFFull)
-            return fail(SHF_ERR_OFFSET_OVERFLOW, "bins per chunk < 2^32",
-                        "HistogramStartOffset is 32 bits wide; this chunk has too many bins");
-        b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
-    }
-    const size_t total = (size_t)b->chunk_base[n_chunks];
-    SHF_CUDA(b->bins.ensure(std::max<size_t>(total, 1) * sizeof(shf_bin)));
-    SHF_CUDA(cudaMemcpyAsync(b->chunkbase.p, b->chunk_base.data(), (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
-    tls_h2d += (size_t)(n_chunks + 1) * 8;
+
+    // ---- vertical scan + bins per row ----
+    st = dispatch_chain(K, b, g, s, 0);
+    if (st != SHF_OK) return st;
+    st = size_output(b, g, h_totals, s);
+    if (st != SHF_OK) return st;
 
     // ---- emitting march ----
     SHF_CUDA(b->mark(5, s));
     st = dispatch_chain(K, b, g, s, 1);
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(6, s));
-    b->ev_valid = g_profiling != 0;
-    b->n_chunks = n_chunks;
-    b->n_bins = total;
-    b->n_offsets = n_off;
-    b->has_result = true;
-    b->on_host = false;
-    return SHF_OK;
+    return publish(b, g);
 }
 
 int bind_device(const shf_filter* f, shf_buffer* b) {

@@ -17,6 +17,10 @@ CASES = [
     dict(w=30, h=30, nn=(3, 3), r=14, b=7, kind="sparse_ids", seed=12),
     dict(w=64, h=64, nn=(3, 3), r=64, b=64, kind="iid", seed=13),
     dict(w=96, h=40, nn=(3, 3), r=20, b=10, kind="blocky", seed=14),
+    # radius above 126 (window counts need more than 8 bits) and the reference benchmark's radius 162
+    dict(w=20, h=16, nn=(15, 17), r=128, b=40, kind="iid", seed=15),
+    dict(w=24, h=18, nn=(15, 19), r=162, b=5, kind="blocky", seed=16),
+    dict(w=20, h=16, nn=(15, 17), r=128, b=600, kind="rare", seed=17),
 ]
 
 

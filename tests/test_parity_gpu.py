@@ -114,6 +114,44 @@ def test_medium(shf, filt, oracle_mod, w, h, r, biomes, kind):
     buf.close()
 
 
+@pytest.mark.parametrize("w,h,r,biomes,kind", [
+    (130, 96, 128, 12, "blocky"),    # 2r+1 = 257: window counts no longer fit 8 bits
+    (192, 192, 162, 5, "iid"),       # the reference benchmark's largest radius (STPTestHistogram.cpp:266-279)
+    (64, 48, 8, 1000, "iid"),        # more than 256 distinct values in one neighbourhood
+    (130, 96, 128, 1024, "iid"),     # BASELINE.json C5 corner: radius 128 x 1024 biomes
+    (96, 64, 64, 1024, "blocky"),
+    (40, 40, 20, 5000, "iid"),
+    (140, 30, 130, 300, "stripes"),
+    (36, 150, 128, 400, "hstripes"),
+    (64, 64, 32, 700, "rare"),
+])
+def test_wide_path(shf, filt, oracle_mod, w, h, r, biomes, kind):
+    """Shapes outside the register-list march (radius above 126 or more than 256 distinct values): shf_generic.cuh."""
+    rng = np.random.default_rng(w * 7919 + h * 31 + r)
+    nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
+    m = random_map(rng, w, h, biomes, kind, nn)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+    assert_same(got, oracle_mod.run_port(m, (w, h), nn, r), f"wide {w}x{h} r={r} B={biomes} {kind}")
+    assert buf.lastPlan()["k_sets"] == 0  # the wide path ran
+    buf.close()
+
+
+def test_wide_path_batch(shf, filt, oracle_mod):
+    rng = np.random.default_rng(77)
+    w, h, r = 48, 40, 16
+    maps = [random_map(rng, w, h, b, k) for b, k in ((900, "iid"), (3, "blocky"), (300, "rare"))]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0x00)
+    hist = filt.runBatch(maps, nn_info(shf, w, h), buf, r)
+    base = buf.chunkBase()
+    per = w * h + 1
+    for i, m in enumerate(maps):
+        got = (hist.Bin["Item"][base[i]:base[i + 1]].copy(), hist.Bin["Weight"][base[i]:base[i + 1]].copy(),
+               hist.HistogramStartOffset[i * per:(i + 1) * per].copy())
+        assert_same(got, oracle_mod.run_port(m, (w, h), (3, 3), r), f"wide batch chunk {i}")
+    buf.close()
+
+
 def test_sparse_ids_and_non_square_neighbourhood(shf, filt, oracle_mod):
     # sample values are arbitrary uint16 (SHF.cpp:404-410 grows its dictionary to max id + 1)
     rng = np.random.default_rng(5)
@@ -225,7 +263,10 @@ def test_c3_batch_properties_and_sampled_chunks(shf, filt, oracle_mod):
     buf.close()
 
 
-@pytest.mark.parametrize("index", range(14))
+from golden.cases import CASES as GOLDEN_CASES
+
+
+@pytest.mark.parametrize("index", range(len(GOLDEN_CASES)))
 def test_against_stored_reference_outputs(shf, filt, index):
     """CUDA path vs outputs of the reference's own compiled filter, committed in tests/golden/ref_vectors.npz."""
     import os
@@ -238,10 +279,5 @@ def test_against_stored_reference_outputs(shf, filt, index):
     info = shf.STPNearestNeighbourInformation((case["w"], case["h"]), case["nn"],
                                               (case["w"] * case["nn"][0], case["h"] * case["nn"][1]))
     buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
-    if case["b"] > 256 and index == 9:
-        # more than 256 distinct samples in one neighbourhood: the wide-list kernel is not built yet
-        with pytest.raises(shf.STPUnsupportedError):
-            filt(make_case(case), info, buf, case["r"])
-    else:
-        assert_same(split_result(filt(make_case(case), info, buf, case["r"])), want, f"golden case {index}")
+    assert_same(split_result(filt(make_case(case), info, buf, case["r"])), want, f"golden case {index}")
     buf.close()

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -150,26 +151,50 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));
-        // one warp per row; shrink the CTA until its two mask rows per warp fit
-        uint32_t warps = 4;
-        const size_t per_warp = (size_t)3 * g.PW * K * 4;
-        while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
-        if (per_warp > 200 * 1024) return fail(SHF_ERR_UNSUPPORTED, "row masks fit shared memory", "map too wide");
-        SHF_CUDA(cudaFuncSetAttribute(shf::rowcount_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(warps * per_warp)));
-        shf::rowcount_kernel<K><<<dim3((g.H + warps - 1) / warps, g.n_chunks), warps * 32, warps * per_warp, s>>>(
-            g, b->colmask.as<uint32_t>(), b->rowtotal.as<uint32_t>());
+        // a warp stages `rows` rows of masks plus their suffix ORs; lanes own (row, block of 2r+1 columns, mask word)
+        shf::RowcountPlan rp{};
+        rp.nblk = (g.PW + g.span - 1u) / g.span;
+        const uint32_t chains = rp.nblk * K;
+        rp.rows = std::max(1u, std::min(32u / chains, g.H));
+        rp.stride = g.PW * K;
+        if (rp.rows > 1u) rp.stride += (32u + 32u / rp.rows - rp.stride % 32u) % 32u;  // rows land on different banks
+        const size_t per_warp = ((size_t)2 * rp.rows * rp.stride + 32u) * 4;
+        uint32_t warps = 2;
+        while (warps > 1 && warps * per_warp > 100 * 1024) warps >>= 1;
+        while (rp.rows > 1u && warps * (((size_t)2 * rp.rows * rp.stride + 32u) * 4) > 200 * 1024) rp.rows--;
+        const size_t rsmem = warps * (((size_t)2 * rp.rows * rp.stride + 32u) * 4);
+        if (rsmem > 200 * 1024) return fail(SHF_ERR_UNSUPPORTED, "row masks fit shared memory", "map too wide");
+        SHF_CUDA(cudaFuncSetAttribute(shf::rowcount_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        const uint32_t rows_per_cta = warps * rp.rows;
+        shf::rowcount_kernel<K><<<dim3((g.H + rows_per_cta - 1) / rows_per_cta, g.n_chunks), warps * 32, rsmem, s>>>(
+            g, rp, b->colmask.as<uint32_t>(), b->rowtotal.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
     } else {
+        Geo gd = g;
+        if (g.flags & 2u) {  // measurement only: cycle counters of the march kernel printed to stderr
+            SHF_CUDA(b->gstate.ensure(64));
+            SHF_CUDA(cudaMemsetAsync(b->gstate.p, 0, 64, s));
+            gd.dbg = b->gstate.as<unsigned long long>();
+        }
         const size_t smem = march_smem(g.TY, g.R, K);
         SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shf::march_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
-            g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
+            gd, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
             b->dict.as<uint16_t>(), 32 * K, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(),
             b->hso.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
+        if (gd.dbg) {
+            unsigned long long h[8];
+            SHF_CUDA(cudaMemcpyAsync(h, gd.dbg, sizeof(h), cudaMemcpyDeviceToHost, s));
+            SHF_CUDA(cudaStreamSynchronize(s));
+            const double cw = (double)g.T * g.n_chunks * g.TY, pw = (double)g.T * g.n_chunks * g.producers;
+            fprintf(stderr,
+                    "[shf dbg] per consumer warp: %.0f cycles, waiting for producers %.0f, list changes %.0f cycles in %.1f events; "
+                    "per producer warp: %.0f cycles, waiting for consumers %.0f, producing %.0f\n",
+                    h[0] / cw, h[1] / cw, h[5] / cw, h[6] / cw, h[2] / pw, h[3] / pw, h[4] / pw);
+        }
     }
     return SHF_OK;
 }
@@ -316,6 +341,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     g.in_row_stride = in_row_stride;
     g.in_chunk_stride = in_chunk_stride;
     g.inv_total = 1.0f / (float)(g.span * g.span);
+    if (const char* e = getenv("SHF_DEBUG_FLAGS")) g.flags = (uint32_t)atoi(e);  // measurement toggles only
     if (W == 0u || H == 0u || n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "W*H*n_chunks > 0", "empty input");
     if (n_chunks > 65535u) return fail(SHF_ERR_UNSUPPORTED, "n_chunks <= 65535", "too many chunks in one batch");
     if (g.PH >= 65535u) return fail(SHF_ERR_UNSUPPORTED, "H + 2*radius < 65535", "map too tall for 16-bit row keys");

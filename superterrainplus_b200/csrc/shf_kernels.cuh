@@ -42,6 +42,8 @@ struct Geo {
     uint32_t producers;            // producer warps of the march kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
+    uint32_t flags;                // bit 0: do not use the packed short-list path (A/B measurements)
+    unsigned long long* dbg;       // measurement only: cycle counters of the march kernel, or null
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -241,45 +243,83 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
 
 // ------------------------------------------------------------------------------------------------------------------
 // bins per row without building any histogram: a pixel's bin count is the popcount of the OR of its window's column
-// masks (the count is order-free, so this is exact by construction). One warp per row; the sliding OR of width 2r+1 is
-// assembled from power-of-two windows (binary decomposition of the width) in shared memory.
+// masks (the count is order-free, so this is exact by construction). The sliding OR of width span = 2r+1 is evaluated
+// the van Herk / Gil-Werman way: columns are cut into blocks of `span`; with suf(i) = OR of block start..end from i on
+// and pre(i) = OR of the block up to i, the window [x, x+span-1] is suf(x) | pre(x+span-1). A lane owns one chain
+// (row, block, mask word): it builds the suffix of its block backwards, then walks forwards combining it with the
+// running prefix of the next block. Two shared-memory ops per mask word and pass instead of a log-step tree.
 // ------------------------------------------------------------------------------------------------------------------
+struct RowcountPlan {
+    uint32_t nblk;      // blocks of `span` columns per row
+    uint32_t rows;      // rows one warp handles at a time
+    uint32_t stride;    // words between two rows of a warp's staging area (padded against bank conflicts)
+};
+
 template <int K>
-__global__ void __launch_bounds__(128) rowcount_kernel(Geo g, const uint32_t* __restrict__ colmask,
-                                                       uint32_t* __restrict__ rowtotal) {
+__global__ void __launch_bounds__(64) rowcount_kernel(Geo g, RowcountPlan rp, const uint32_t* __restrict__ colmask,
+                                                      uint32_t* __restrict__ rowtotal) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t y = blockIdx.x * (blockDim.x >> 5) + warp, n = blockIdx.y;
-    if (y >= g.H) return;
-    const uint32_t PW = g.PW, NW = PW * K;  // a row of masks as NW words, mask i = words [i*K, i*K+K)
-    uint32_t* pa = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 3 * NW;  // window of length 2^k at i (ping)
-    uint32_t* pb = pa + NW;                                                    // (pong)
-    uint32_t* acc = pb + NW;                                                   // window of length L at i
-    const uint32_t* src = colmask + ((size_t)n * g.H + y) * NW;
-    for (uint32_t i = lane; i < NW; i += 32u) {
-        pa[i] = src[i];
-        acc[i] = 0u;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
+    const uint32_t n = blockIdx.y;
+    const uint32_t PW = g.PW, NW = PW * K, span = g.span;
+    const uint32_t y0 = (blockIdx.x * n_warps + warp) * rp.rows;
+    if (y0 >= g.H) return;
+    const uint32_t rows = min(rp.rows, g.H - y0);
+    uint32_t* org = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * (2u * rp.rows * rp.stride + 32u);
+    uint32_t* suf = org + (size_t)rp.rows * rp.stride;
+    uint32_t* tot = suf + (size_t)rp.rows * rp.stride;  // [rows] bins per row
+    for (uint32_t r = 0u; r < rows; r++) {
+        const uint32_t* src = colmask + ((size_t)n * g.H + y0 + r) * NW;
+        for (uint32_t i = lane; i < NW; i += 32u) org[r * rp.stride + i] = src[i];
+    }
+    if (lane < rp.rows) tot[lane] = 0u;
+    __syncwarp();
+    const uint32_t chains = rp.nblk * K;
+    for (uint32_t q = lane; q < rows * chains; q += 32u) {  // suffix ORs, written next to the masks
+        const uint32_t r = q / chains, ch = q - r * chains, blk = ch / K, k = ch - blk * K;
+        const uint32_t lo = blk * span, hi = min(lo + span, PW);
+        const uint32_t* a = org + r * rp.stride + k;
+        uint32_t* s2 = suf + r * rp.stride + k;
+        uint32_t acc = 0u;
+        for (uint32_t i = hi; i > lo;) {  // 8 loads in flight per trip: the chain itself is only register ORs
+            const uint32_t m = min(8u, i - lo);
+            uint32_t v[8];
+#pragma unroll
+            for (uint32_t j = 0u; j < 8u; j++) v[j] = j < m ? a[(i - 1u - j) * K] : 0u;
+#pragma unroll
+            for (uint32_t j = 0u; j < 8u; j++) {
+                acc |= v[j];
+                if (j < m) s2[(i - 1u - j) * K] = acc;
+            }
+            i -= m;
+        }
     }
     __syncwarp();
-    uint32_t L = 0u;
-    for (uint32_t bit = 1u; bit <= g.span; bit <<= 1) {
-        if (g.span & bit) {  // acc(i) |= pow(i + L): extends every window from length L to L + bit
-            for (uint32_t i = lane; i + L * K < NW; i += 32u) acc[i] |= pa[i + L * K];
-            L += bit;
+    for (uint32_t q = lane; q < rows * chains; q += 32u) {  // windows starting in my block
+        const uint32_t r = q / chains, ch = q - r * chains, blk = ch / K, k = ch - blk * K;
+        const uint32_t lo = blk * span, hi = min(lo + span, g.W);  // only windows of real pixels
+        const uint32_t* nxt = org + r * rp.stride + (size_t)(lo + span) * K + k;  // next block's masks
+        const uint32_t* s2 = suf + r * rp.stride + k;
+        uint32_t pre = 0u, total = 0u;
+        for (uint32_t x = lo; x < hi;) {
+            const uint32_t m = min(8u, hi - x);
+            uint32_t sv[8], nv[8];
+#pragma unroll
+            for (uint32_t j = 0u; j < 8u; j++) {
+                sv[j] = j < m ? s2[(x + j) * K] : 0u;
+                nv[j] = j < m ? nxt[(x - lo + j) * K] : 0u;  // column x + j + span joins the prefix of the next window
+            }
+#pragma unroll
+            for (uint32_t j = 0u; j < 8u; j++) {
+                if (j < m) total += __popc(sv[j] | pre);
+                pre |= nv[j];
+            }
+            x += m;
         }
-        if ((bit << 1) <= g.span) {  // pow'(i) = pow(i) | pow(i + bit)
-            const uint32_t sh = bit * K;
-            for (uint32_t i = lane; i < NW; i += 32u) pb[i] = pa[i] | (i + sh < NW ? pa[i + sh] : 0u);
-            uint32_t* t = pa;
-            pa = pb;
-            pb = t;
-        }
-        __syncwarp();
+        if (hi > lo) atomicAdd(&tot[r], total);
     }
-    uint32_t total = 0u;
-    for (uint32_t i = lane; i < g.W * K; i += 32u) total += __popc(acc[i]);
-    total = __reduce_add_sync(kFull, total);
-    if (lane == 0u) rowtotal[(size_t)n * g.H + y] = total;
+    __syncwarp();
+    if (lane < rows) rowtotal[(size_t)n * g.H + y0 + lane] = tot[lane];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -387,6 +427,7 @@ __global__ void __launch_bounds__(640, 1)
         for (uint32_t t = warp - TY; t < n_batches * PPB; t += NP) {
             const uint32_t b = t / PPB, pass = t % PPB;
             const uint32_t s = b % stages, cb = b * NB;
+            const long long tp0 = g.dbg ? clock64() : 0;
             const uint32_t slot0 = cb % R;  // ring slot of the batch's first column
             const uint32_t cu = pass * CPP + colq;
             const bool live = cb + cu < PW;
@@ -403,6 +444,7 @@ __global__ void __launch_bounds__(640, 1)
                 so[i] = cm[(size_t)po * g.P + c];
             }
             if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);  // batch b - stages is consumed
+            const long long tp1 = g.dbg ? clock64() : 0;
             uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -421,6 +463,12 @@ __global__ void __launch_bounds__(640, 1)
             __threadfence_block();
             __syncwarp();
             if (lane == 0u) mbar_arrive(&full_bar[s]);
+            if (g.dbg && lane == 0u) {
+                const long long tp2 = clock64();
+                atomicAdd(&g.dbg[2], (unsigned long long)(tp2 - tp0));
+                atomicAdd(&g.dbg[3], (unsigned long long)(tp1 - tp0));
+                atomicAdd(&g.dbg[4], (unsigned long long)(tp2 - tp1));
+            }
         }
         return;
     }
@@ -428,6 +476,7 @@ __global__ void __launch_bounds__(640, 1)
     // =============================== consumer warps ===============================
     const uint32_t y = y0 + warp;
     const bool row_active = y < g.H;
+    const long long tw0 = g.dbg ? clock64() : 0;
     uint8_t* crow = cring + (size_t)warp * R * CS;
     uint32_t* mbuf = mbuf_all + (size_t)warp * NB * K;
     uint32_t* sA = scratch + (size_t)warp * 2 * E;
@@ -444,8 +493,10 @@ __global__ void __launch_bounds__(640, 1)
         listmask[k] = 0u;
     }
     uint32_t n = 0u;       // bins in the list
+    // packed view of a short list (n <= 16): the lanes >= n of set 0 replicate entry lane % n, so that S = 32 / n
+    // consecutive pixels are produced by one pass over the warp (lane = step slot * n + entry)
+    uint32_t pk_steps = 0u, pk_entry = 0u, pk_slot = 0u, pk_off = 0u;  // pk_off: my entry's byte in the slot's count vector
     uint32_t rowpos = 0u;  // bins emitted so far in this row
-    uint32_t hso_reg = 0u;
     const uint32_t row_first = row_active ? rowbase[(size_t)n_chunk * g.H + y] : 0u;
     uint2* dst = bins + (row_active ? (size_t)chunkbase[n_chunk] + row_first : (size_t)0) + lane;
     uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
@@ -461,11 +512,24 @@ __global__ void __launch_bounds__(640, 1)
     for (uint32_t b = 0u; b < n_batches; b++) {
         const uint32_t s = b % stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
+        const long long tc0 = g.dbg ? clock64() : 0;
         mbar_wait(&full_bar[s], (b / stages) & 1u);
+        if (g.dbg && lane == 0u) atomicAdd(&g.dbg[1], (unsigned long long)(clock64() - tc0));
         if (row_active) {
             if (lane < (uint32_t)NB) {
 #pragma unroll
                 for (int k = 0; k < K; k++) mbuf[lane * K + k] = mnext[k];
+            }
+            // bit i: column cb + i holds a biome that is not in the list (a birth is due there); kept current after
+            // every change of the list, so the fast paths test a register instead of re-reading the masks
+            uint32_t born_cols;
+            {
+                uint32_t w = 0u;
+#pragma unroll
+                for (int k = 0; k < K; k++) w |= mnext[k] & ~listmask[k];
+                born_cols = __ballot_sync(kFull, w != 0u && lane < (uint32_t)NB);
+            }
+            if (lane < (uint32_t)NB) {
                 const uint32_t cn = cb + NB + lane;
 #pragma unroll
                 for (int k = 0; k < K; k++) mnext[k] = cn < PW ? cmask_row[(size_t)cn * K + k] : 0u;
@@ -473,94 +537,111 @@ __global__ void __launch_bounds__(640, 1)
             __syncwarp();
             uint32_t c = cb;
             while (c < ce) {
-                // a segment: no ring wrap, constant has_out / emit, inside one group of 32 output pixels
+                // a segment: no ring wrap, constant has_out / emit
                 uint32_t seg_end = min(ce, c + (R - in_slot));
                 const bool has_out = c >= span, emit = c >= two_r;
                 seg_end = has_out ? min(seg_end, c + (R - out_slot)) : min(seg_end, span);
-                seg_end = emit ? min(seg_end, c + 32u - ((c - two_r) & 31u)) : min(seg_end, two_r);
+                if (!emit) seg_end = min(seg_end, two_r);
                 const uint8_t* pin = crow + (size_t)in_slot * CS;
                 const uint8_t* pout = crow + (size_t)out_slot * CS;
-                const uint32_t* pm = mbuf + (size_t)(c - cb) * K;
                 uint32_t steps = seg_end - c;
+                uint32_t rel = c - cb;   // column of the next step inside the batch
                 uint32_t x = c - two_r;  // only meaningful when emit
                 while (steps > 0u) {
-                    if (steps >= 4u && has_out && emit) {
-                        // ---------------- fast path: four steps without any birth or death ----------------
-                        uint32_t c1[K], c2[K], c3[K], c4[K];
-                        uint32_t bornany = 0u;
-                        bool bad = false;
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const uint8_t* gi = pin + id[k];
-                            const uint8_t* go = pout + id[k];
-                            c1[k] = cnt[k] + gi[0] - go[0];
-                            c2[k] = c1[k] + gi[CS] - go[CS];
-                            c3[k] = c2[k] + gi[2 * CS] - go[2 * CS];
-                            c4[k] = c3[k] + gi[3 * CS] - go[3 * CS];
-                            bornany |= (pm[k] | pm[K + k] | pm[2 * K + k] | pm[3 * K + k]) & ~listmask[k];
-                            bad |= ((uint32_t)(k * 32) + lane < n) && min(min(c1[k], c2[k]), min(c3[k], c4[k])) == 0u;
+                    const uint32_t births = born_cols >> rel;
+                    if (pk_steps >= 2u && steps >= 2u && has_out && emit) {
+                        // ---------------- packed fast path: min(S, steps) pixels of a short list at once ----------------
+                        const uint32_t sn = min(pk_steps, steps);
+                        if ((births & ((1u << sn) - 1u)) == 0u) {
+                            const bool act = pk_slot < sn;
+                            int32_t d = 0;
+                            if (act) d = (int32_t)pin[pk_off] - (int32_t)pout[pk_off];
+                            for (uint32_t off = 1u, sh = n; off < sn; off <<= 1, sh <<= 1) {  // running sum over my entry's slots
+                                const int32_t t = __shfl_up_sync(kFull, d, sh);
+                                if (pk_slot >= off) d += t;
+                            }
+                            const uint32_t cj = cnt[0] + (uint32_t)d;  // count of my entry after step pk_slot
+                            if (!__any_sync(kFull, act && cj == 0u)) {
+                                if (act) *dst = make_uint2(hi[0], __float_as_uint(__fmul_rn(__uint2float_rn(cj), inv)));
+                                if (lane < sn) hso_row[x + lane] = row_first + rowpos + lane * n;
+                                cnt[0] = __shfl_sync(kFull, cj, (sn - 1u) * n + pk_entry);
+                                dst += sn * n;
+                                rowpos += sn * n;
+                                x += sn;
+                                rel += sn;
+                                steps -= sn;
+                                pin += sn * CS;
+                                pout += sn * CS;
+                                continue;
+                            }
                         }
-                        if (!__any_sync(kFull, bad) && bornany == 0u) {
+                    } else if (steps >= 4u && has_out && emit) {
+                        // ---------------- fast path: four steps without any birth or death ----------------
+                        if ((births & 0xFu) == 0u) {
+                            uint32_t c1[K], c2[K], c3[K], c4[K];
+                            bool bad = false;
 #pragma unroll
                             for (int k = 0; k < K; k++) {
-                                if ((uint32_t)(k * 32) + lane < n) {
-                                    uint2* d = dst + k * 32;
-                                    d[0] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c1[k]), inv)));
-                                    d[n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c2[k]), inv)));
-                                    d[2u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c3[k]), inv)));
-                                    d[3u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c4[k]), inv)));
+                                const uint8_t* gi = pin + id[k];
+                                const uint8_t* go = pout + id[k];
+                                c1[k] = cnt[k] + gi[0] - go[0];
+                                c2[k] = c1[k] + gi[CS] - go[CS];
+                                c3[k] = c2[k] + gi[2 * CS] - go[2 * CS];
+                                c4[k] = c3[k] + gi[3 * CS] - go[3 * CS];
+                                bad |= ((uint32_t)(k * 32) + lane < n) && min(min(c1[k], c2[k]), min(c3[k], c4[k])) == 0u;
+                            }
+                            if (!__any_sync(kFull, bad)) {
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                    if ((uint32_t)(k * 32) + lane < n) {
+                                        uint2* d = dst + k * 32;
+                                        d[0] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c1[k]), inv)));
+                                        d[n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c2[k]), inv)));
+                                        d[2u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c3[k]), inv)));
+                                        d[3u * n] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(c4[k]), inv)));
+                                    }
+                                    cnt[k] = c4[k];
                                 }
-                                cnt[k] = c4[k];
+                                if (lane < 4u) hso_row[x + lane] = row_first + rowpos + lane * n;
+                                dst += 4u * n;
+                                rowpos += 4u * n;
+                                x += 4u;
+                                rel += 4u;
+                                steps -= 4u;
+                                pin += 4 * CS;
+                                pout += 4 * CS;
+                                continue;
                             }
-                            const uint32_t t = (lane - x) & 31u;
-                            if (t < 4u) hso_reg = row_first + rowpos + t * n;
-                            dst += 4u * n;
-                            rowpos += 4u * n;
-                            x += 4u;
-                            if ((x & 31u) == 0u || x == g.W) {
-                                if (lane <= ((x - 1u) & 31u)) hso_row[((x - 1u) & ~31u) + lane] = hso_reg;
-                            }
-                            steps -= 4u;
-                            pin += 4 * CS;
-                            pout += 4 * CS;
-                            pm += 4 * K;
-                            continue;
                         }
                     } else if (steps >= 4u && !has_out && !emit) {
                         // ---------------- fast path while the window fills: counts only grow, no pixel yet ----------------
-                        uint32_t bornany = 0u;
-#pragma unroll
-                        for (int k = 0; k < K; k++)
-                            bornany |= (pm[k] | pm[K + k] | pm[2 * K + k] | pm[3 * K + k]) & ~listmask[k];
-                        if (bornany == 0u) {
+                        if ((births & 0xFu) == 0u) {
 #pragma unroll
                             for (int k = 0; k < K; k++) {
                                 const uint8_t* gi = pin + id[k];
                                 cnt[k] += (uint32_t)gi[0] + gi[CS] + gi[2 * CS] + gi[3 * CS];
                             }
+                            rel += 4u;
                             steps -= 4u;
                             pin += 4 * CS;
                             pout += 4 * CS;
-                            pm += 4 * K;
                             continue;
                         }
                     }
                     // ---------------- one step, any case ----------------
                     {
                         bool deadp = false;
-                        uint32_t bornany = 0u;
-                        uint32_t born[K];
 #pragma unroll
                         for (int k = 0; k < K; k++) {
                             uint32_t v = cnt[k] + pin[id[k]];
                             if (has_out) v -= pout[id[k]];
                             cnt[k] = v;
-                            born[k] = pm[k] & ~listmask[k];
-                            bornany |= born[k];
                             deadp |= ((uint32_t)(k * 32) + lane < n) && v == 0u;
                         }
-                        if (__any_sync(kFull, deadp) || bornany != 0u) {
-                            const uint32_t c_now = seg_end - steps;
+                        const bool has_birth = (births & 1u) != 0u;
+                        if (__any_sync(kFull, deadp) || has_birth) {
+                            const long long ts0 = g.dbg ? clock64() : 0;
+                            const uint32_t c_now = cb + rel;
                             // (1) drop dead bins, keeping the order of the survivors (SHF.cpp:435-445)
                             {
                                 uint32_t keep_base = 0u;
@@ -594,35 +675,47 @@ __global__ void __launch_bounds__(640, 1)
                             }
                             // (2) append the bins born in this column, ordered by their vertical chain start
                             //     (SHF.cpp:411-415: the column's own bin order is the horizontal pass's insertion order)
-                            uint32_t nb = 0u;
-#pragma unroll
-                            for (int k = 0; k < K; k++) nb += __popc(born[k]);
-                            if (nb) {
+                            if (has_birth) {
                                 uint32_t pending[K];
+                                uint32_t nb = 0u;
 #pragma unroll
-                                for (int k = 0; k < K; k++) pending[k] = born[k];
-                                uint32_t found = 0u;
-                                // walk the window rows of the column bottom-up, 32 rows at a time: the lowest occurrence
-                                // of a biome carries its chain start in vstart
-                                for (uint32_t blk = 0u; blk * 32u < span && found < nb; blk++) {
-                                    const int32_t off = (int32_t)two_r - (int32_t)(blk * 32u + lane);
-                                    const bool valid = off >= 0;
-                                    const size_t at = (size_t)(y + (valid ? off : 0)) * g.P + c_now;
-                                    const uint32_t sv = valid ? (uint32_t)cm[at] : 0xFFFFu;
-                                    const bool inpend = valid && test_bit<K>(pending, sv);
-                                    const unsigned same = __match_any_sync(kFull, sv);
-                                    const bool first = inpend && ((uint32_t)(__ffs(same) - 1) == lane);
-                                    const unsigned fm = __ballot_sync(kFull, first);
-                                    if (first) {
-                                        const uint32_t idx = found + __popc(fm & lanemask_lt());
-                                        sA[idx] = ((uint32_t)sdict[sv] << 16) | sv;
-                                        sB[idx] = ((uint32_t)vs[at] << 16) | (uint32_t)pin[sv];
+                                for (int k = 0; k < K; k++) {
+                                    pending[k] = mbuf[rel * K + k] & ~listmask[k];
+                                    nb += __popc(pending[k]);
+                                }
+                                // the window rows of the column, bottom-up, 32 rows per block: every occurrence of a
+                                // biome inside one window carries the same chain start in vstart. All loads go out
+                                // together (2r+1 <= 255 here, so at most 8 blocks).
+                                uint32_t cell[8];
+#pragma unroll
+                                for (int blk = 0; blk < 8; blk++) {
+                                    const int32_t off = (int32_t)two_r - (int32_t)(blk * 32 + lane);
+                                    cell[blk] = 0xFFFFu;
+                                    if (off >= 0) {
+                                        const size_t at = (size_t)(y + off) * g.P + c_now;
+                                        cell[blk] = ((uint32_t)vs[at] << 16) | (uint32_t)cm[at];
                                     }
-                                    found += __popc(fm);
+                                }
+                                uint32_t found = 0u;
 #pragma unroll
-                                    for (int k = 0; k < K; k++) {
-                                        const uint32_t mine = (first && (sv >> 5) == (uint32_t)k) ? (1u << (sv & 31u)) : 0u;
-                                        pending[k] &= ~__reduce_or_sync(kFull, mine);
+                                for (int blk = 0; blk < 8; blk++) {
+                                    if ((uint32_t)(blk * 32) < span && found < nb) {
+                                        const uint32_t sv = cell[blk] & 0xFFFFu;
+                                        const bool inpend = sv != 0xFFFFu && test_bit<K>(pending, sv);
+                                        const unsigned same = __match_any_sync(kFull, sv);
+                                        const bool first = inpend && ((uint32_t)(__ffs(same) - 1) == lane);
+                                        const unsigned fm = __ballot_sync(kFull, first);
+                                        if (first) {
+                                            const uint32_t idx = found + __popc(fm & lanemask_lt());
+                                            sA[idx] = ((uint32_t)sdict[sv] << 16) | sv;
+                                            sB[idx] = (cell[blk] & 0xFFFF0000u) | (uint32_t)pin[sv];
+                                        }
+                                        found += __popc(fm);
+#pragma unroll
+                                        for (int k = 0; k < K; k++) {
+                                            const uint32_t mine = (first && (sv >> 5) == (uint32_t)k) ? (1u << (sv & 31u)) : 0u;
+                                            pending[k] &= ~__reduce_or_sync(kFull, mine);
+                                        }
                                     }
                                 }
                                 __syncwarp();
@@ -664,7 +757,7 @@ __global__ void __launch_bounds__(640, 1)
                                 n += nb;
                                 __syncwarp();
                             }
-                            // (3) membership mask of the list
+                            // (3) membership mask of the list, columns of this batch that still hold a stranger
 #pragma unroll
                             for (int kk = 0; kk < K; kk++) {
                                 uint32_t mine = 0u;
@@ -675,6 +768,29 @@ __global__ void __launch_bounds__(640, 1)
                                 }
                                 listmask[kk] = __reduce_or_sync(kFull, mine);
                             }
+                            {
+                                uint32_t w = 0u;
+                                if (lane < (uint32_t)NB) {
+#pragma unroll
+                                    for (int k = 0; k < K; k++) w |= mbuf[lane * K + k] & ~listmask[k];
+                                }
+                                born_cols = __ballot_sync(kFull, w != 0u);
+                            }
+                            // (4) packed view of a short list
+                            pk_steps = 0u;
+                            if (n >= 1u && n <= 16u && !(g.flags & 1u)) {
+                                pk_steps = 32u / n;
+                                pk_slot = lane / n;
+                                pk_entry = lane - pk_slot * n;
+                                id[0] = __shfl_sync(kFull, id[0], pk_entry);
+                                hi[0] = __shfl_sync(kFull, hi[0], pk_entry);
+                                cnt[0] = __shfl_sync(kFull, cnt[0], pk_entry);
+                                pk_off = pk_slot * CS + id[0];
+                            }
+                            if (g.dbg && lane == 0u) {
+                                atomicAdd(&g.dbg[5], (unsigned long long)(clock64() - ts0));
+                                atomicAdd(&g.dbg[6], 1ull);
+                            }
                         }
                         if (emit) {
 #pragma unroll
@@ -682,18 +798,15 @@ __global__ void __launch_bounds__(640, 1)
                                 if ((uint32_t)(k * 32) + lane < n)
                                     dst[k * 32] = make_uint2(hi[k], __float_as_uint(__fmul_rn(__uint2float_rn(cnt[k]), inv)));
                             }
-                            if ((x & 31u) == lane) hso_reg = row_first + rowpos;
+                            if (lane == 0u) hso_row[x] = row_first + rowpos;
                             dst += n;
                             rowpos += n;
                             x += 1u;
-                            if ((x & 31u) == 0u || x == g.W) {
-                                if (lane <= ((x - 1u) & 31u)) hso_row[((x - 1u) & ~31u) + lane] = hso_reg;
-                            }
                         }
+                        rel += 1u;
                         steps -= 1u;
                         pin += CS;
                         pout += CS;
-                        pm += K;
                     }
                 }
                 const uint32_t adv = seg_end - c;
@@ -715,6 +828,7 @@ __global__ void __launch_bounds__(640, 1)
             if (lane == 0u) mbar_arrive(&empty_bar[s]);
         }
     }
+    if (g.dbg && lane == 0u) atomicAdd(&g.dbg[0], (unsigned long long)(clock64() - tw0));
 }
 
 // ------------------------------------------------------------------------------------------------------------------

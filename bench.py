@@ -37,6 +37,15 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "filtered_mpixels_per_s"
 UNIT = "Mpixels/s"
 
@@ -57,6 +66,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
+                    help="torch.distributed backend of the barrier / max-over-ranks plumbing (no data-path collective)")
     return ap.parse_args()
 
 
@@ -231,7 +242,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -252,7 +263,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
 
     def barrier():
         if world > 1:
@@ -262,7 +276,7 @@ def run_ours(args):
     def max_over_ranks(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device="cuda" if args.backend == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -396,7 +410,7 @@ def run_ours(args):
             "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "impl": "ours",
         }
-        print(json.dumps(line))
+        emit(line)
     buf.close()
     filt.close()
     if world > 1:
@@ -405,6 +419,11 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: anything a library prints (e.g. NCCL's version banner) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -102,6 +102,39 @@ SHF_API int shf_buffer_read_device(const shf_buffer* buffer, const shf_bin** bin
 /* Host array of n_chunks+1 first-bin indices (last = total bins) of the last result. */
 SHF_API int shf_buffer_chunk_base(const shf_buffer* buffer, const uint64_t** chunk_base, uint32_t* n_chunks);
 
+/* ---- device-side consumer of the histogram (additive) ----
+ * The multi-biome heightfield of SuperDemo+/Script/STPMultiHeightGenerator.cu:35-71, computed from the DEVICE-RESIDENT
+ * result of the last shf_run_device / shf_run_batch / shf_run on a buffer, so that bins and offsets never travel to the
+ * host and back (the copy at SuperDemo+/World/Biomes/STPBiomefieldGenerator.cpp:108-123 disappears):
+ *   height(x, y) = sum over the pixel's bins in bin order of Weight * (simplex2DFractal(x, y; biome) * Variation + Depth)
+ * with simplex2DFractal as in SuperAlgorithm+/Device/Private/STPSimplexNoise.cu:84-109. */
+
+/* Layout-identical to STPDemo::STPBiomeProperty (SuperDemo+/World/Biomes/STPBiomeProperty.hpp:10-27). */
+typedef struct shf_biome_property {
+    float scale;
+    uint32_t octave;
+    float persistence;
+    float lacunarity;
+    float depth;
+    float variation;
+} shf_biome_property;
+
+typedef struct shf_heightfield shf_heightfield; /* tables of one generator, uploaded once */
+
+/* table[i] = properties of sample value i (the reference's __constant__ BiomeTable, STPMultiHeightGenerator.cu:14);
+ * bins whose item is >= n_table contribute nothing. permutation: 512 bytes (a permutation of 0..255, repeated) and
+ * gradient2d: 2 * gradient2d_size floats, as produced by STPPermutationGenerator (SuperAlgorithm+/Host/Private/
+ * STPPermutationGenerator.cpp:40-93) -- all three are HOST pointers, copied to the filter's device. */
+SHF_API int shf_heightfield_create(shf_heightfield** out, shf_filter* filter, const shf_biome_property* table,
+                                   uint32_t n_table, const unsigned char* permutation, const float* gradient2d,
+                                   uint32_t gradient2d_size);
+SHF_API void shf_heightfield_destroy(shf_heightfield* generator);
+/* Heightfields of chunks [first_chunk, first_chunk + n_chunks) of the buffer's last result. offsets_xy: HOST array of
+ * 2 * n_chunks floats (the `offset` argument of the reference kernel per chunk). height_dev: DEVICE pointer, n_chunks
+ * blocks of MapSize.x * MapSize.y floats, row-major. `stream` is a cudaStream_t; returns once the work is enqueued. */
+SHF_API int shf_heightfield_run(shf_heightfield* generator, shf_buffer* buffer, uint32_t first_chunk, uint32_t n_chunks,
+                                const float* offsets_xy, float* height_dev, void* stream);
+
 /* Message of the last failure on the calling thread: "<expression>: <description>" in the spirit of
  * STPException::STPBasic::what(), so that the C++ shim can throw the matching exception type. */
 SHF_API const char* shf_last_error(void);

@@ -5,10 +5,14 @@ Importable only from tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-
 """
 from .pyoracle import (  # noqa: F401
     BIN_DTYPE,
+    BIOME_PROPERTY_DTYPE,
     OracleError,
     build,
     closed_form,
+    have_height_reference,
     have_reference,
+    heightfield_port,
+    heightfield_reference,
     reference_pinned_active,
     run_port,
     run_reference,

@@ -228,3 +228,75 @@ def closed_form(sample_map, map_size, nn, radius):
             offsets.append(len(items))
     return (np.array(items, dtype=np.uint16), np.array(weights, dtype=np.float32),
             np.array(offsets, dtype=np.uint32))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# heightfield consumer
+# ----------------------------------------------------------------------------------------------------------------------
+_HF_PORT_SO = os.path.join(_HERE, "libshf_heightfield_oracle.so")
+_HF_REF_SO = os.path.join(_HERE, "_ref", "libshf_ref_height.so")
+# STPDemo::STPBiomeProperty (SuperDemo+/World/Biomes/STPBiomeProperty.hpp:10-27)
+BIOME_PROPERTY_DTYPE = np.dtype([("Scale", "<f4"), ("Octave", "<u4"), ("Persistence", "<f4"), ("Lacunarity", "<f4"),
+                                 ("Depth", "<f4"), ("Variation", "<f4")])
+_hf_port = None
+_hf_ref = None
+
+
+def _pack_bins(items, weights):
+    bins = np.zeros(len(items), dtype=BIN_DTYPE)
+    bins["item"] = items
+    bins["weight"] = weights
+    return bins
+
+
+def _hf_args(items, weights, offsets, map_size, table, permutation, gradient, offset_xy):
+    w, h = map_size
+    bins = _pack_bins(items, weights)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint32)
+    table = np.ascontiguousarray(table, dtype=BIOME_PROPERTY_DTYPE)
+    perm = np.ascontiguousarray(permutation, dtype=np.uint8)
+    grad = np.ascontiguousarray(gradient, dtype=np.float32).reshape(-1)
+    assert perm.size == 512 and offs.size == w * h + 1 and grad.size % 2 == 0
+    return bins, offs, table, perm, grad, np.zeros(w * h, dtype=np.float32)
+
+
+def heightfield_port(items, weights, offsets, map_size, table, permutation, gradient, offset_xy, pixels=None) -> np.ndarray:
+    """CPU restatement (oracle/shf_heightfield_oracle.c) of the multi-biome heightfield of one chunk, float32 [H, W].
+    pixels = (begin, end) restricts the evaluation to that pixel range (the rest stays 0)."""
+    global _hf_port
+    if _hf_port is None:
+        if not os.path.exists(_HF_PORT_SO):
+            build()
+        _hf_port = ctypes.CDLL(_HF_PORT_SO)
+        _hf_port.shf_heightfield_oracle.restype = None
+    bins, offs, table, perm, grad, out = _hf_args(items, weights, offsets, map_size, table, permutation, gradient, offset_xy)
+    vp = ctypes.c_void_p
+    _hf_port.shf_heightfield_oracle(vp(bins.ctypes.data), vp(offs.ctypes.data), ctypes.c_uint32(map_size[0]),
+                                    ctypes.c_uint32(map_size[1]), vp(table.ctypes.data), ctypes.c_uint32(len(table)),
+                                    vp(perm.ctypes.data), vp(grad.ctypes.data), ctypes.c_uint32(grad.size // 2),
+                                    ctypes.c_float(offset_xy[0]), ctypes.c_float(offset_xy[1]), vp(out.ctypes.data),
+                                    ctypes.c_uint32(pixels[0] if pixels else 0),
+                                    ctypes.c_uint32(pixels[1] if pixels else map_size[0] * map_size[1]))
+    return out.reshape(map_size[1], map_size[0])
+
+
+def have_height_reference() -> bool:
+    return os.path.exists(_HF_REF_SO)
+
+
+def heightfield_reference(items, weights, offsets, map_size, table, permutation, gradient, offset_xy) -> np.ndarray:
+    """The reference's own device code (oracle/_ref/libshf_ref_height.so); needs a GPU."""
+    global _hf_ref
+    if _hf_ref is None:
+        _hf_ref = ctypes.CDLL(_HF_REF_SO)
+        _hf_ref.ref_heightfield_run.restype = ctypes.c_int
+    bins, offs, table, perm, grad, out = _hf_args(items, weights, offsets, map_size, table, permutation, gradient, offset_xy)
+    vp = ctypes.c_void_p
+    st = _hf_ref.ref_heightfield_run(vp(bins.ctypes.data), vp(offs.ctypes.data), ctypes.c_uint64(len(bins)),
+                                     ctypes.c_uint32(map_size[0]), ctypes.c_uint32(map_size[1]), vp(table.ctypes.data),
+                                     ctypes.c_uint32(len(table)), vp(perm.ctypes.data), vp(grad.ctypes.data),
+                                     ctypes.c_uint32(grad.size // 2), ctypes.c_float(offset_xy[0]),
+                                     ctypes.c_float(offset_xy[1]), vp(out.ctypes.data))
+    if st != 0:
+        raise OracleError(st, "reference heightfield (CUDA)")
+    return out.reshape(map_size[1], map_size[0])

@@ -10,8 +10,10 @@ the CUDA library and a device and raises otherwise.
 """
 from .api import (  # noqa: F401
     BIN_DTYPE,
+    BIOME_PROPERTY_DTYPE,
     STPCUDAError,
     STPInvalidEnum,
+    STPMultiBiomeHeightfield,
     STPNearestNeighbourInformation,
     STPNumericDomainError,
     STPSingleHistogram,
@@ -22,6 +24,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BIN_DTYPE", "STPCUDAError", "STPInvalidEnum", "STPNearestNeighbourInformation", "STPNumericDomainError",
+    "BIN_DTYPE", "BIOME_PROPERTY_DTYPE", "STPCUDAError", "STPMultiBiomeHeightfield", "STPInvalidEnum", "STPNearestNeighbourInformation", "STPNumericDomainError",
     "STPSingleHistogram", "STPSingleHistogramFilter", "STPUnsupportedError", "library", "library_path",
 ]

@@ -22,6 +22,10 @@ _LIB_NAME = "libshf_b200.so"
 # STPSingleHistogram::STPBin: {uint16 Item; float Weight}, 8 bytes with 2 bytes of padding after Item
 BIN_DTYPE = np.dtype({"names": ["Item", "Weight"], "formats": ["<u2", "<f4"], "offsets": [0, 4], "itemsize": 8})
 
+# STPDemo::STPBiomeProperty (SuperDemo+/World/Biomes/STPBiomeProperty.hpp:10-27), 24 bytes
+BIOME_PROPERTY_DTYPE = np.dtype([("Scale", "<f4"), ("Octave", "<u4"), ("Persistence", "<f4"), ("Lacunarity", "<f4"),
+                                 ("Depth", "<f4"), ("Variation", "<f4")])
+
 SHF_OK, SHF_ERR_NUMERIC_DOMAIN, SHF_ERR_INVALID_ENUM, SHF_ERR_CUDA = 0, 1, 2, 3
 SHF_ERR_OFFSET_OVERFLOW, SHF_ERR_UNSUPPORTED, SHF_ERR_INVALID_ARGUMENT = 4, 5, 6
 
@@ -30,7 +34,7 @@ C_ABI_SYMBOLS = (
     "shf_filter_create", "shf_filter_destroy", "shf_buffer_create", "shf_buffer_destroy", "shf_buffer_read",
     "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
-    "shf_set_profiling", "shf_buffer_phase_ms",
+    "shf_set_profiling", "shf_buffer_phase_ms", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
 )
 PHASES = ("dictionary", "remap_vscan", "rowcount", "rowscan", "host_gap", "march_emit")
 
@@ -98,6 +102,10 @@ def library() -> ctypes.CDLL:
     lib.shf_set_profiling.argtypes = [ctypes.c_int]
     lib.shf_set_profiling.restype = None
     lib.shf_buffer_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
+    lib.shf_heightfield_create.argtypes = [P(vp), vp, vp, u32, vp, vp, u32]
+    lib.shf_heightfield_destroy.argtypes = [vp]
+    lib.shf_heightfield_destroy.restype = None
+    lib.shf_heightfield_run.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -279,3 +287,43 @@ class STPSingleHistogramFilter:
 
 
 STPFilterBuffer = STPSingleHistogramFilter.STPFilterBuffer
+
+
+class STPMultiBiomeHeightfield:
+    """Device-side consumer of a filter result: the multi-biome heightfield kernel of
+    SuperDemo+/Script/STPMultiHeightGenerator.cu:35-71 (generateMultiBiomeHeightmap) reading the histogram where the
+    filter left it in device memory (additive; shf_heightfield_*).
+
+    table: BIOME_PROPERTY_DTYPE array indexed by sample value (the reference's __constant__ BiomeTable);
+    permutation: 512 uint8; gradient: [N, 2] float32 (STPPermutationGenerator's tables, taken as inputs)."""
+
+    def __init__(self, filt: STPSingleHistogramFilter, table, permutation, gradient):
+        table = np.ascontiguousarray(table, dtype=BIOME_PROPERTY_DTYPE)
+        perm = np.ascontiguousarray(permutation, dtype=np.uint8)
+        grad = np.ascontiguousarray(gradient, dtype=np.float32).reshape(-1)
+        if perm.size != 512 or grad.size % 2:
+            raise ValueError("permutation must hold 512 bytes and gradient N x 2 floats")
+        self._h = ctypes.c_void_p()
+        _check(library().shf_heightfield_create(ctypes.byref(self._h), filt._h, table.ctypes.data, len(table),
+                                                perm.ctypes.data, grad.ctypes.data, grad.size // 2))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            library().shf_heightfield_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, filter_buffer: STPFilterBuffer, first_chunk: int, n_chunks: int, offsets_xy,
+                 height_device_ptr: int, stream: int = 0) -> None:
+        """Heightfields of chunks [first_chunk, first_chunk + n_chunks) of the buffer's last result into device memory
+        (n_chunks x H x W float32); enqueued on `stream`."""
+        off = np.ascontiguousarray(offsets_xy, dtype=np.float32).reshape(-1)
+        if off.size != 2 * n_chunks:
+            raise ValueError("offsets_xy must hold one (x, y) pair per chunk")
+        _check(library().shf_heightfield_run(self._h, filter_buffer._h, first_chunk, n_chunks, off.ctypes.data,
+                                             height_device_ptr, stream))

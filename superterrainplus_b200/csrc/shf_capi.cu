@@ -3,6 +3,7 @@
 #include "../../include/shf_b200.h"
 #include "shf_kernels.cuh"
 #include "shf_generic.cuh"
+#include "shf_heightfield.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -92,6 +93,13 @@ struct shf_filter {
     size_t smem_optin = 0;
 };
 
+struct shf_heightfield {
+    int device = 0;
+    size_t smem_optin = 0;
+    uint32_t n_table = 0, grad_size = 0;
+    DevBuf table, perm, grad;
+};
+
 struct shf_buffer {
     unsigned char exec_type = SHF_EXEC_PARALLEL;
     int device = -1;
@@ -100,8 +108,9 @@ struct shf_buffer {
         bins, hso, gstate;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
-    uint32_t n_chunks = 0;
+    uint32_t n_chunks = 0, last_w = 0, last_h = 0;
     size_t n_bins = 0, n_offsets = 0;
+    DevBuf hf_offsets;  // per-chunk noise offsets of shf_heightfield_run
     bool has_result = false, on_host = false;
     uint32_t plan_k = 0, plan_ty = 0, plan_biomes = 0, plan_smem = 0;
     cudaEvent_t ev[kPhases + 1] = {};
@@ -121,7 +130,7 @@ struct shf_buffer {
         }
         ev_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
-                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate};
+                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -273,6 +282,8 @@ int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s)
 int publish(shf_buffer* b, const Geo& g) {
     b->ev_valid = g_profiling != 0;
     b->n_chunks = g.n_chunks;
+    b->last_w = g.W;
+    b->last_h = g.H;
     b->n_bins = (size_t)b->chunk_base[g.n_chunks];
     b->n_offsets = (size_t)g.n_chunks * ((size_t)g.W * g.H + 1u);
     b->has_result = true;
@@ -605,6 +616,82 @@ int shf_buffer_chunk_base(const shf_buffer* b, const uint64_t** chunk_base, uint
     if (!b || !chunk_base || !n_chunks) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
     *chunk_base = b->has_result ? b->chunk_base.data() : nullptr;
     *n_chunks = b->has_result ? b->n_chunks : 0u;
+    return SHF_OK;
+}
+
+int shf_heightfield_create(shf_heightfield** out, shf_filter* f, const shf_biome_property* table, uint32_t n_table,
+                           const unsigned char* permutation, const float* gradient2d, uint32_t gradient2d_size) {
+    if (!out || !f || !table || !permutation || !gradient2d)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    *out = nullptr;
+    if (n_table == 0u || gradient2d_size == 0u)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "n_table > 0 && gradient2d_size > 0", "empty table");
+    const size_t smem = 512 + (size_t)gradient2d_size * 8 + (size_t)n_table * sizeof(shf_biome_property);
+    if (smem > f->smem_optin)
+        return fail(SHF_ERR_UNSUPPORTED, "tables fit shared memory", "biome / gradient tables too large for one CTA");
+    SHF_CUDA(cudaSetDevice(f->device));
+    shf_heightfield* h = new (std::nothrow) shf_heightfield();
+    if (!h) return fail(SHF_ERR_INVALID_ARGUMENT, "new shf_heightfield", "out of host memory");
+    h->device = f->device;
+    h->smem_optin = f->smem_optin;
+    h->n_table = n_table;
+    h->grad_size = gradient2d_size;
+    cudaError_t e = h->table.ensure((size_t)n_table * sizeof(shf_biome_property));
+    if (e == cudaSuccess) e = h->perm.ensure(512);
+    if (e == cudaSuccess) e = h->grad.ensure((size_t)gradient2d_size * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(h->table.p, table, (size_t)n_table * sizeof(shf_biome_property), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->perm.p, permutation, 512, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->grad.p, gradient2d, (size_t)gradient2d_size * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        shf_heightfield_destroy(h);
+        return fail(SHF_ERR_CUDA, "upload of the generator tables", cudaGetErrorString(e));
+    }
+    tls_h2d += (size_t)n_table * sizeof(shf_biome_property) + 512 + (size_t)gradient2d_size * 8;
+    *out = h;
+    return SHF_OK;
+}
+
+void shf_heightfield_destroy(shf_heightfield* h) {
+    if (!h) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    h->table.release();
+    h->perm.release();
+    h->grad.release();
+    if (prev >= 0) cudaSetDevice(prev);
+    delete h;
+}
+
+int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk, uint32_t n_chunks, const float* offsets_xy,
+                        float* height_dev, void* stream) {
+    if (!h || !b || !offsets_xy || !height_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (!b->has_result) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer holds a result", "run the filter on this buffer first");
+    if (b->device != h->device) return fail(SHF_ERR_INVALID_ARGUMENT, "same device", "histogram and generator live on different devices");
+    if (n_chunks == 0u || first_chunk > b->n_chunks || n_chunks > b->n_chunks - first_chunk || n_chunks > 65535u)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "chunk range inside the last result", "no such chunks");
+    SHF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SHF_CUDA(b->hf_offsets.ensure((size_t)n_chunks * 8));
+    SHF_CUDA(cudaMemcpyAsync(b->hf_offsets.p, offsets_xy, (size_t)n_chunks * 8, cudaMemcpyHostToDevice, s));
+    tls_h2d += (size_t)n_chunks * 8;
+    shf::HeightGeo g{};
+    g.W = b->last_w;
+    g.H = b->last_h;
+    g.n_table = h->n_table;
+    g.grad_size = h->grad_size;
+    g.half_x = (float)g.W / 2.0f;
+    g.half_y = (float)g.H / 2.0f;
+    const size_t smem = 512 + (size_t)h->grad_size * 8 + (size_t)h->n_table * sizeof(shf_biome_property);
+    SHF_CUDA(cudaFuncSetAttribute(shf::heightfield_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t npx = g.W * g.H;
+    const uint32_t gx = std::max(1u, std::min((npx + 255u) / 256u, 148u * 8u));
+    shf::heightfield_kernel<<<dim3(gx, n_chunks), 256, smem, s>>>(
+        g, b->bins.as<uint2>(), b->hso.as<uint32_t>(), b->chunkbase.as<uint64_t>(), first_chunk,
+        h->table.as<shf_biome_property>(), h->perm.as<unsigned char>(), h->grad.as<float>(), b->hf_offsets.as<float2>(),
+        height_dev);
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
     return SHF_OK;
 }
 

@@ -28,3 +28,23 @@ def assert_same(got, want, what=""):
         b = int(np.flatnonzero(gb != wb)[0])
         px = int(np.searchsorted(wo, b, side="right") - 1)
         raise AssertionError(f"{what}: weight bits differ at bin {b} (pixel {px}): got {gw[b]!r} want {ww[b]!r}")
+
+
+def make_generator_tables(seed, n_table, grad_size=12, max_octave=8):
+    """Inputs of the heightfield consumer: biome property table, 512-byte permutation, unit-gradient table. The reference
+    derives the last two from std::mt19937_64 + std::shuffle (STPPermutationGenerator.cpp:40-93), which is standard-
+    library defined, so they are treated as inputs here: any permutation of 0..255 repeated twice, gradients evenly
+    spread on the unit circle."""
+    rng = np.random.default_rng(seed)
+    table = np.zeros(n_table, dtype=[("Scale", "<f4"), ("Octave", "<u4"), ("Persistence", "<f4"), ("Lacunarity", "<f4"),
+                                     ("Depth", "<f4"), ("Variation", "<f4")])
+    table["Scale"] = rng.uniform(40.0, 900.0, n_table)
+    table["Octave"] = rng.integers(1, max_octave + 1, n_table)
+    table["Persistence"] = rng.uniform(0.3, 0.7, n_table)
+    table["Lacunarity"] = rng.uniform(1.7, 2.6, n_table)
+    table["Depth"] = rng.uniform(0.0, 1.0, n_table)
+    table["Variation"] = rng.uniform(0.05, 1.0, n_table)
+    perm = np.tile(rng.permutation(256).astype(np.uint8), 2)
+    angle = np.arange(grad_size, dtype=np.float64) * (2.0 * np.pi / grad_size) + float(rng.uniform(0, 1))
+    grad = np.stack([np.cos(angle), np.sin(angle)], axis=1).astype(np.float32)
+    return table, perm, grad

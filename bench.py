@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--heightfield", action="store_true",
+                    help="also time the device-side consumer (multi-biome heightfield) on the resident histograms")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
                     help="torch.distributed backend of the barrier / max-over-ranks plumbing (no data-path collective)")
     return ap.parse_args()
@@ -334,6 +336,35 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
                 "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
+    # ---- device-side consumer on the resident result (BASELINE.json config 4 chain) ----
+    consumer = None
+    if args.heightfield:
+        rng = np.random.default_rng(7)
+        table = np.zeros(wl.biomes, dtype=api.BIOME_PROPERTY_DTYPE)
+        table["Scale"], table["Octave"] = rng.uniform(100.0, 900.0, wl.biomes), 8
+        table["Persistence"], table["Lacunarity"] = 0.5, 2.0
+        table["Depth"], table["Variation"] = rng.uniform(0.0, 1.0, wl.biomes), rng.uniform(0.1, 1.0, wl.biomes)
+        perm = np.tile(rng.permutation(256).astype(np.uint8), 2)
+        ang = np.arange(12) * (2 * np.pi / 12)
+        gen = pkg.STPMultiBiomeHeightfield(filt, table, perm, np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32))
+        heights = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
+        offs = np.zeros((n, 2), dtype=np.float32)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3 + args.steps):
+            if i == 3:
+                h0.record()
+            for first in range(0, n, 65535):
+                cnt = min(65535, n - first)
+                gen(buf, first, cnt, offs[first:first + cnt], heights[first].data_ptr(), stream)
+        h1.record()
+        torch.cuda.synchronize()
+        hms = h0.elapsed_time(h1) / args.steps
+        consumer = {"kernel": "heightfield_kernel", "ms": hms, "mpixels_per_s": n * w * h / (hms * 1e-3) / 1e6,
+                    "octaves": 8, "bins_per_pixel": n_bins / (n * w * h),
+                    "chain_ms": ms_step + hms, "chain_mpixels_per_s": n * w * h / ((ms_step + hms) * 1e-3) / 1e6}
+        gen.close()
+        del heights
+
     # ---- end to end: host buffers in, page-locked host histograms out ----
     e2e = None
     if not args.no_e2e:
@@ -407,7 +438,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic",
             "config": {**config_of(wl, world), "plan": plan, "bins_per_pixel": n_bins / (n * w * h)},
-            "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e, "consumer": consumer,
             "gpu_launches": launches, "clocks": clocks, "impl": "ours",
         }
         emit(line)

@@ -2,6 +2,7 @@
 // sequence of the kernels in shf_kernels.cuh. No torch, no CPU compute path: every result comes from the kernels.
 #include "../../include/shf_b200.h"
 #include "shf_kernels.cuh"
+#include "shf_events.cuh"
 #include "shf_generic.cuh"
 #include "shf_heightfield.cuh"
 
@@ -105,7 +106,7 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
-        bins, hso, gstate;
+        bins, hso, gstate, evpool, rowinfo;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
     uint32_t n_chunks = 0, last_w = 0, last_h = 0;
@@ -130,7 +131,8 @@ struct shf_buffer {
         }
         ev_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
-                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets};
+                       &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
+                       &evpool, &rowinfo};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -148,6 +150,35 @@ size_t march_smem(uint32_t ty, uint32_t R, int K) {
     return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2 + 128;
 }
 
+size_t emit_smem(uint32_t ty, uint32_t R, int K) {
+    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K) + (size_t)ty * shf::emit_act_cap(K) * 8 + 128;
+}
+
+constexpr uint32_t kLegacyMarch = 4u;  // SHF_DEBUG_FLAGS bit: the list-maintaining march_kernel instead of events + emit
+
+template <int K>
+int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
+    unsigned long long* counter = b->chunktotal.as<unsigned long long>() + g.n_chunks;
+    SHF_CUDA(cudaMemsetAsync(counter, 0, 8, s));
+    shf::events_kernel<K><<<dim3((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks), shf::kEventWarps * 32, 0, s>>>(
+        g, b->colmask.as<uint32_t>(), b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->dict.as<uint16_t>(), 32 * K,
+        b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), counter, b->rowinfo.as<uint2>(),
+        b->rowtotal.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    return SHF_OK;
+}
+
+int dispatch_events(int K, shf_buffer* b, const Geo& g, cudaStream_t s) {
+    switch (K) {
+        case 1: return launch_events<1>(b, g, s);
+        case 2: return launch_events<2>(b, g, s);
+        case 4: return launch_events<4>(b, g, s);
+        case 8: return launch_events<8>(b, g, s);
+    }
+    return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
+}
+
 // phase 0: vertical scan + bins per row; phase 1: the emitting march
 template <int K>
 int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
@@ -160,6 +191,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));
+        if (!(g.flags & kLegacyMarch)) return launch_events<K>(b, g, s);
         // a warp stages `rows` rows of masks plus their suffix ORs; lanes own (row, block of 2r+1 columns, mask word)
         shf::RowcountPlan rp{};
         rp.nblk = (g.PW + g.span - 1u) / g.span;
@@ -177,6 +209,14 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         const uint32_t rows_per_cta = warps * rp.rows;
         shf::rowcount_kernel<K><<<dim3((g.H + rows_per_cta - 1) / rows_per_cta, g.n_chunks), warps * 32, rsmem, s>>>(
             g, rp, b->colmask.as<uint32_t>(), b->rowtotal.as<uint32_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    } else if (!(g.flags & kLegacyMarch)) {
+        const size_t smem = emit_smem(g.TY, g.R, K);
+        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::emit_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+            b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
     } else {
@@ -238,7 +278,7 @@ int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec
     SHF_CUDA(b->dict.ensure((size_t)g.n_chunks * g.Bpad * 2));
     SHF_CUDA(b->rowtotal.ensure((size_t)g.n_chunks * g.H * 4));
     SHF_CUDA(b->rowbase.ensure((size_t)g.n_chunks * g.H * 4));
-    SHF_CUDA(b->chunktotal.ensure((size_t)g.n_chunks * 8));
+    SHF_CUDA(b->chunktotal.ensure((size_t)(g.n_chunks + 1) * 8));  // + the event counter
     SHF_CUDA(b->chunkbase.ensure((size_t)(g.n_chunks + 1) * 8));
     SHF_CUDA(b->hso.ensure((size_t)g.n_chunks * ((size_t)g.W * g.H + 1u) * 4));
     const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), g.n_chunks);
@@ -254,7 +294,7 @@ int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec
 }
 
 // bins per row -> first bin of every row, chunk totals on the host (u32 overflow check), the bin buffer
-int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s) {
+int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s, bool with_events = false) {
     const uint32_t n_chunks = g.n_chunks;
     SHF_CUDA(b->mark(3, s));
     shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
@@ -262,9 +302,21 @@ int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s)
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
     SHF_CUDA(b->mark(4, s));
-    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
-    tls_d2h += (size_t)n_chunks * 8;
+    const size_t n_read = (size_t)n_chunks + (with_events ? 1u : 0u);
+    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, n_read * 8, cudaMemcpyDeviceToHost, s));
+    tls_d2h += n_read * 8;
     SHF_CUDA(cudaStreamSynchronize(s));
+    if (with_events) {
+        // the event pool is sized by guess; a call that needs more grows it and builds the event lists again
+        const uint64_t need = h_totals[n_chunks];
+        if (need > 0xFFFFFFFFull)
+            return fail(SHF_ERR_UNSUPPORTED, "presence chains per call < 2^32", "too many bin births in one batch");
+        if (need > b->evpool.cap / 8) {
+            SHF_CUDA(b->evpool.ensure((size_t)(need + need / 8u + 1024u) * 8));
+            const int st = dispatch_events((int)g.K, b, g, s);
+            if (st != SHF_OK) return st;
+        }
+    }
     b->chunk_base.assign(n_chunks + 1u, 0ull);
     for (uint32_t i = 0; i < n_chunks; i++) {
         if (h_totals[i] > 0xFFFFFFFFull)
@@ -360,7 +412,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
-    SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 16));
+    SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 64));
     uint32_t* h_nbiomes = b->h_small.as<uint32_t>();
     uint64_t* h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
 
@@ -405,7 +457,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             g.stages = (np + ppb - 1u) / ppb + extra;
             g.R = g.span + shf::kMarchNB * g.stages;
         };
-        auto smem_of = [&](uint32_t t) { return march_smem(t, g.R, K); };
+        auto smem_of = [&](uint32_t t) { return (g.flags & kLegacyMarch) ? march_smem(t, g.R, K) : emit_smem(t, g.R, K); };
         plan(4u, 2u);
         if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
         if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
@@ -427,13 +479,18 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
 
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
     SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * g.PW * K * 4));
+    const bool events = !(g.flags & kLegacyMarch);
+    if (events) {
+        SHF_CUDA(b->rowinfo.ensure((size_t)n_chunks * H * 8));
+        SHF_CUDA(b->evpool.ensure((size_t)n_chunks * H * 32u * (K + 1) * 8));
+    }
     int st = prepare_common(b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
 
     // ---- vertical scan + bins per row ----
     st = dispatch_chain(K, b, g, s, 0);
     if (st != SHF_OK) return st;
-    st = size_output(b, g, h_totals, s);
+    st = size_output(b, g, h_totals, s, events);
     if (st != SHF_OK) return st;
 
     // ---- emitting march ----

@@ -1,0 +1,538 @@
+// shf_events.cuh -- the event-list formulation of the horizontal pass (the default path for up to 256 distinct values).
+//
+// The reference's horizontal accumulator (SHF.cpp:608-679) keeps a bin for a sample value from the column where the
+// value enters the sliding window until the step in which its count returns to zero (SHF.cpp:435-445); a value that
+// re-enters later gets a NEW bin at the end of the list (SHF.cpp:411-415). So along one output row every sample value
+// owns a sequence of "presence chains": maximal runs of columns holding the value in their vertical window with gaps of
+// at most 2r+1 columns. Each chain is one EVENT (value, birth column c_b, last presence column c_l):
+//   * the chain's bin exists for the pixels x with  max(c_b - 2r, 0) <= x <= min(c_l, W - 1)
+//   * a pixel lists the bins of the events alive at x, ordered by birth: (c_b, vertical chain start of the value in
+//     column c_b) -- the second key is the order of the column's own intermediate histogram (SHF.cpp:522-563).
+// events_kernel builds the sorted event list of every row from the per-(row, column) presence masks of vscan_kernel and
+// totals the bins per row (which replaces a counting march). emit_kernel then needs no sequential list maintenance at
+// all: a pixel's bins are the alive events in list order (warp ballot + popc gives the position), the counts come from
+// a dense per-row horizontal sliding sum kept next to the shared-memory ring of vertical window counts.
+#pragma once
+#include "shf_kernels.cuh"
+
+namespace shf {
+
+constexpr int kEventWarps = 4;          // rows per CTA of events_kernel
+constexpr uint32_t kEventStage = 192;   // events of one row staged in shared memory before their pool slot is known
+constexpr uint32_t kNoEvent = 0xFFFFFFFFu;
+
+// Event record, 8 bytes: x = compact id | sample value << 16, y = first pixel | (last pixel + 1) << 16
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+    // lane i holds row i of a 32x32 bit matrix; afterwards lane i holds column i (bit r = former row r, bit i)
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t other = __shfl_xor_sync(kFull, x, j);
+        x = (lane & (uint32_t)j) ? ((x & ~m) | ((other >> j) & m)) : ((x & m) | ((other << j) & ~m));
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
+// One pass over the row's presence masks. Writes at most `cap` records to `dst` (shared staging or the row's pool
+// slot); returns the number of events and adds the row's bins to `bins_total` (per-lane partial sums).
+template <int K>
+__device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t lane, const uint32_t* __restrict__ cmask_row,
+                                             const uint16_t* __restrict__ cm, const uint16_t* __restrict__ vs,
+                                             const uint32_t (&item)[K], uint16_t* tab, uint2* dst, uint32_t cap,
+                                             uint32_t& bins_total) {
+    const uint32_t PW = g.PW, span = g.span, two_r = 2u * g.r, W = g.W;
+    int32_t last[K];
+    uint32_t open[K], openxb[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        last[k] = -1;
+        open[k] = kNoEvent;
+        openxb[k] = 0u;
+    }
+    uint32_t E = 0u;
+    const uint32_t n_words = (PW + 31u) / 32u;
+    uint32_t mnext[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) mnext[k] = lane < PW ? cmask_row[(size_t)lane * K + k] : 0u;
+    for (uint32_t w = 0u; w < n_words; w++) {
+        const uint32_t c0 = w * 32u;
+        uint32_t rem[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) rem[k] = mnext[k];
+        {
+            const uint32_t cn = c0 + 32u + lane;
+#pragma unroll
+            for (int k = 0; k < K; k++) mnext[k] = cn < PW ? cmask_row[(size_t)cn * K + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) rem[k] = transpose32(rem[k], lane);  // lane = compact id 32k + lane, bit j = column c0 + j
+        for (;;) {
+            // every lane advances to its next birth inside this word
+            uint32_t bj[K], jmin = 32u;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                bj[k] = 32u;
+                while (rem[k]) {
+                    const uint32_t j = (uint32_t)__ffs((int)rem[k]) - 1u;
+                    const int32_t c = (int32_t)(c0 + j);
+                    if (last[k] < 0 || c - last[k] > (int32_t)span) {
+                        bj[k] = j;
+                        break;
+                    }
+                    if (span >= 32u) {  // the rest of the word cannot hold a gap wider than the window
+                        last[k] = (int32_t)(c0 + 31u - (uint32_t)__clz((int)rem[k]));
+                        rem[k] = 0u;
+                    } else {
+                        last[k] = c;
+                        rem[k] &= rem[k] - 1u;
+                    }
+                }
+                jmin = min(jmin, bj[k]);
+            }
+            jmin = __reduce_min_sync(kFull, jmin);
+            if (jmin == 32u) break;
+            const uint32_t c = c0 + jmin;
+            // the values born in column c
+            bool mem[K];
+            unsigned mb[K];
+            uint32_t gsz = 0u;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                mem[k] = bj[k] == jmin;
+                mb[k] = __ballot_sync(kFull, mem[k]);
+                gsz += (uint32_t)__popc(mb[k]);
+            }
+            uint32_t rank[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) rank[k] = 0u;
+            if (gsz > 1u) {
+                // order them by the start row of their vertical chain: every cell of the column's window publishes the
+                // chain start of its value (all cells of one value inside a window agree)
+                for (uint32_t o = lane; o < span; o += 32u) {
+                    const size_t at = (size_t)(y + o) * g.P + c;
+                    tab[cm[at]] = vs[at];
+                }
+                __syncwarp();
+                uint32_t vk[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) vk[k] = mem[k] ? (uint32_t)tab[k * 32 + lane] : 0u;
+#pragma unroll
+                for (int kk = 0; kk < K; kk++) {
+                    unsigned m2 = mb[kk];
+                    while (m2) {
+                        const int l = __ffs((int)m2) - 1;
+                        const uint32_t v = __shfl_sync(kFull, vk[kk], l);
+#pragma unroll
+                        for (int k = 0; k < K; k++) rank[k] += (v < vk[k]) ? 1u : 0u;
+                        m2 &= m2 - 1u;
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (mem[k]) {
+                    if (open[k] != kNoEvent) {  // the previous chain of this value ended at column last[k]
+                        const uint32_t xd = min((uint32_t)last[k] + 1u, W);
+                        if (open[k] < cap) dst[open[k]].y = openxb[k] | (xd << 16);
+                        bins_total += xd - openxb[k];
+                    }
+                    const uint32_t idx = E + rank[k];
+                    const uint32_t xb = c > two_r ? c - two_r : 0u;
+                    if (idx < cap) dst[idx] = make_uint2((uint32_t)(k * 32) + lane | (item[k] << 16), xb);
+                    open[k] = idx;
+                    openxb[k] = xb;
+                    if (span >= 32u) {
+                        last[k] = (int32_t)(c0 + 31u - (uint32_t)__clz((int)rem[k]));
+                        rem[k] = 0u;
+                    } else {
+                        last[k] = (int32_t)c;
+                        rem[k] &= rem[k] - 1u;
+                    }
+                }
+            }
+            E += gsz;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (open[k] != kNoEvent) {
+            const uint32_t xd = min((uint32_t)last[k] + 1u, W);
+            if (open[k] < cap) dst[open[k]].y = openxb[k] | (xd << 16);
+            bins_total += xd - openxb[k];
+        }
+    }
+    return E;
+}
+
+// rowinfo(n, y) = (first record of the row in the pool, number of records). counter[0] = records handed out so far;
+// a row whose slot would end beyond `pool_cap` writes nothing (the host grows the pool and runs the kernel again).
+template <int K>
+__global__ void __launch_bounds__(kEventWarps * 32)
+    events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint16_t* __restrict__ cmap,
+                  const uint16_t* __restrict__ vstart, const uint16_t* __restrict__ dict, uint32_t dict_stride,
+                  uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
+                  uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal) {
+    __shared__ uint2 stage_all[kEventWarps][kEventStage];
+    __shared__ uint16_t tab_all[kEventWarps][32 * K];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.y, y = blockIdx.x * kEventWarps + warp;
+    if (y >= g.H) return;
+    uint2* stage = stage_all[warp];
+    uint16_t* tab = tab_all[warp];
+    const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * g.PW * K;
+    const uint16_t* cm = cmap + (size_t)n * g.PH * g.P;
+    const uint16_t* vs = vstart + (size_t)n * g.PH * g.P;
+    uint32_t item[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const uint32_t id = k * 32 + lane;
+        item[k] = id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
+    }
+    uint32_t bins = 0u;
+    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, stage, kEventStage, bins);
+    bins = __reduce_add_sync(kFull, bins);
+    unsigned long long first = 0ull;
+    if (lane == 0u) first = atomicAdd(counter, (unsigned long long)E);
+    first = __shfl_sync(kFull, first, 0);
+    if (lane == 0u) {
+        rowinfo[(size_t)n * g.H + y] = make_uint2((uint32_t)first, E);
+        rowtotal[(size_t)n * g.H + y] = bins;
+    }
+    if (first + E > pool_cap) return;
+    __syncwarp();
+    if (E <= kEventStage) {
+        for (uint32_t i = lane; i < E; i += 32u) pool[first + i] = stage[i];
+    } else {
+        uint32_t again = 0u;
+        (void)walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, pool + first, E, again);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// emit: producers as in march_kernel (vertical window counts into a shared-memory ring), consumers = one warp per row
+// ------------------------------------------------------------------------------------------------------------------
+// K bytes of one count vector (compact ids lane*K .. lane*K+K-1) widened to 16-bit pairs
+template <int K>
+__device__ __forceinline__ void load_counts(const uint8_t* p, uint32_t (&v)[(K + 1) / 2]) {
+    if (K == 1) {
+        v[0] = *p;
+    } else if (K == 2) {
+        const uint32_t t = *reinterpret_cast<const uint16_t*>(p);
+        v[0] = __byte_perm(t, 0u, 0x4140);
+    } else if (K == 4) {
+        const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+        v[0] = __byte_perm(t, 0u, 0x4140);
+        v[1] = __byte_perm(t, 0u, 0x4342);
+    } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = __byte_perm(t.x, 0u, 0x4140);
+        v[1] = __byte_perm(t.x, 0u, 0x4342);
+        v[2] = __byte_perm(t.y, 0u, 0x4140);
+        v[3] = __byte_perm(t.y, 0u, 0x4342);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void store_sums(uint8_t* p, const uint32_t (&v)[(K + 1) / 2]) {
+    if (K == 1) {
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)v[0];
+    } else if (K == 2) {
+        *reinterpret_cast<uint32_t*>(p) = v[0];
+    } else if (K == 4) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+    } else {
+        *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// shared memory of an emit CTA:
+//   cring[TY][R][32K]  u8   vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
+//   sbuf[TY][16][SS]   u16  horizontal window counts of the batch being emitted, SS = 64K + 16 bytes per pixel
+//   act[TY][64K]       8 B  the events overlapping the pixels being emitted, in list order
+__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + 16u; }
+__host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 64u * (uint32_t)K; }
+
+template <int K>
+__global__ void __launch_bounds__(640, 1)
+    emit_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint8_t* __restrict__ base,
+                const uint2* __restrict__ pool, const uint2* __restrict__ rowinfo, const uint32_t* __restrict__ rowbase,
+                const uint64_t* __restrict__ chunkbase, uint2* __restrict__ bins, uint32_t* __restrict__ hso) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int CS = 32 * K;
+    constexpr int NB = kMarchNB;
+    constexpr int KE = 2 * K;                      // register sets of the active list
+    constexpr uint32_t SS = emit_sbuf_stride(K);
+    constexpr uint32_t ACAP = emit_act_cap(K);
+    constexpr int SR = (K + 1) / 2;
+    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW, stages = g.stages;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
+    const uint32_t y0 = tile * TY;
+    const uint32_t NP = g.producers;
+    const uint32_t n_batches = (PW + NB - 1u) / NB;
+
+    uint8_t* cring = smem;
+    uint8_t* sbuf_all = smem + (size_t)TY * R * CS;
+    uint2* act_all = reinterpret_cast<uint2*>(sbuf_all + (size_t)TY * NB * SS);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(act_all + (size_t)TY * ACAP);
+    uint64_t* empty_bar = full_bar + 8;
+    if (threadIdx.x < stages) {
+        mbar_init(&full_bar[threadIdx.x], (uint32_t)(NB / (32 / (2 * K))));
+        mbar_init(&empty_bar[threadIdx.x], TY);
+    }
+    __syncthreads();
+    const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
+
+    if (warp >= TY) {
+        // =============================== producer warps (see march_kernel) ===============================
+        constexpr int LPC = 2 * K;
+        constexpr int CPP = 32 / LPC;
+        constexpr int PPB = NB / CPP;
+        const uint32_t part = lane % LPC, colq = lane / LPC;
+        const uint32_t tile_rows = min(TY, g.H - y0);
+        const uint32_t bit0 = part * 128u;
+        for (uint32_t t = warp - TY; t < n_batches * PPB; t += NP) {
+            const uint32_t b = t / PPB, pass = t % PPB;
+            const uint32_t s = b % stages, cb = b * NB;
+            const uint32_t slot0 = cb % R;
+            const uint32_t cu = pass * CPP + colq;
+            const bool live = cb + cu < PW;
+            const uint32_t c = live ? cb + cu : PW - 1u;
+            uint32_t slot = slot0 + cu;
+            if (slot >= R) slot -= R;
+            uint4 v = *reinterpret_cast<const uint4*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS + part * 16u);
+            uint32_t sa[16], so[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
+                sa[i] = cm[(size_t)pi * g.P + c];
+                so[i] = cm[(size_t)po * g.P + c];
+            }
+            if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);
+            uint8_t* out = cring + (size_t)slot * CS + part * 16u;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if ((uint32_t)i < tile_rows) {
+                    if (live) *reinterpret_cast<uint4*>(out) = v;
+                    out += (size_t)R * CS;
+                    const uint32_t ba = sa[i] * 8u - bit0, bo = so[i] * 8u - bit0;
+                    v.x += shl_clamp(1u, ba) - shl_clamp(1u, bo);
+                    v.y += shl_clamp(1u, ba - 32u) - shl_clamp(1u, bo - 32u);
+                    v.z += shl_clamp(1u, ba - 64u) - shl_clamp(1u, bo - 64u);
+                    v.w += shl_clamp(1u, ba - 96u) - shl_clamp(1u, bo - 96u);
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0u) mbar_arrive(&full_bar[s]);
+        }
+        return;
+    }
+
+    // =============================== consumer warps ===============================
+    const uint32_t y = y0 + warp;
+    const bool row_active = y < g.H;
+    uint8_t* crow = cring + (size_t)warp * R * CS;
+    uint8_t* sb = sbuf_all + (size_t)warp * NB * SS;
+    uint2* act = act_all + (size_t)warp * ACAP;
+    const uint2 ri = row_active ? rowinfo[(size_t)n_chunk * g.H + y] : make_uint2(0u, 0u);
+    const uint2* ev = pool + ri.x;
+    const uint32_t E = ri.y;
+    uint32_t off = row_active ? rowbase[(size_t)n_chunk * g.H + y] : 0u;  // offset of the next pixel's first bin
+    uint2* dst = bins + (row_active ? (size_t)chunkbase[n_chunk] + off : (size_t)0);
+    uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
+    const float inv = g.inv_total;
+
+    uint32_t srun[SR];
+#pragma unroll
+    for (int i = 0; i < SR; i++) srun[i] = 0u;
+    uint32_t rx[KE], ry[KE];   // the active list: record k*32 + lane, or the packed view in set 0
+#pragma unroll
+    for (int k = 0; k < KE; k++) {
+        rx[k] = 0u;
+        ry[k] = 0xFFFFu;
+    }
+    uint32_t Ea = 0u, e_lo = 0u, valid_until = 0u;
+    bool clean = false;
+    uint32_t pk_n = 0u, pk_slot = 0u, pk_entry = 0u;  // packed view (Ea <= 16): lane = slot * Ea + entry
+
+    uint32_t in_slot = 0u, out_slot = (R - span % R) % R;
+    for (uint32_t b = 0u; b < n_batches; b++) {
+        const uint32_t s = b % stages, cb = b * NB;
+        const uint32_t ce = min(cb + (uint32_t)NB, PW);
+        mbar_wait(&full_bar[s], (b / stages) & 1u);
+        if (row_active) {
+            // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
+            {
+                const uint8_t* pin = crow + (size_t)in_slot * CS + lane * K;
+                const uint8_t* pout = crow + (size_t)out_slot * CS + lane * K;
+                uint32_t si = in_slot, so = out_slot;
+                uint8_t* ps = sb + lane * (2 * K);
+                for (uint32_t c = cb; c < ce; c++) {
+                    uint32_t a[SR];
+                    load_counts<K>(pin, a);
+#pragma unroll
+                    for (int i = 0; i < SR; i++) srun[i] += a[i];
+                    if (c >= span) {
+                        uint32_t o[SR];
+                        load_counts<K>(pout, o);
+#pragma unroll
+                        for (int i = 0; i < SR; i++) srun[i] -= o[i];
+                    }
+                    if (c >= two_r) store_sums<K>(ps, srun);
+                    ps += SS;
+                    pin += CS;
+                    pout += CS;
+                    if (++si == R) {
+                        si = 0u;
+                        pin = crow + lane * K;
+                    }
+                    if (++so == R) {
+                        so = 0u;
+                        pout = crow + lane * K;
+                    }
+                }
+                in_slot = si;
+                out_slot = so;
+            }
+            __syncwarp();
+            // ---- the pixels of this batch: x = c - 2r ----
+            if (ce > two_r) {
+                const uint32_t xa0 = cb > two_r ? cb - two_r : 0u, xe0 = ce - two_r;
+                uint32_t xa = xa0, xe = xe0;
+                bool single = false;
+                while (xa < xe0) {
+                    if (xe > valid_until || single) {
+                        // ---- rebuild the active list for the pixels [xa, xe) ----
+                        uint32_t nact = 0u, vmin = 0xFFFFFFFFu;
+                        bool dirty = false;
+                        __syncwarp();
+                        for (uint32_t eb = e_lo; eb < E; eb += 32u) {
+                            const uint32_t idx = eb + lane;
+                            uint2 rec = make_uint2(0u, 0xFFFFu);
+                            if (idx < E) rec = ev[idx];
+                            const uint32_t xb = rec.y & 0xFFFFu, xd = rec.y >> 16;
+                            const bool in_range = idx < E;
+                            const bool fut = in_range && xb >= xe;
+                            const bool ov = in_range && xb < xe && xd > xa;
+                            const unsigned bm = __ballot_sync(kFull, ov);
+                            if (ov) {
+                                const uint32_t at = nact + (uint32_t)__popc(bm & lanemask_lt());
+                                if (at < ACAP) act[at] = rec;
+                                dirty |= xb > xa || xd < xe;
+                                vmin = min(vmin, xd);
+                            }
+                            if (fut) vmin = min(vmin, xb);
+                            nact += (uint32_t)__popc(bm);
+                            const unsigned deadm = __ballot_sync(kFull, in_range && xd <= xa);
+                            if (eb == e_lo && deadm == kFull) e_lo += 32u;
+                            if (__ballot_sync(kFull, fut || !in_range) == kFull) break;
+                        }
+                        __syncwarp();
+                        if (nact > ACAP && xe - xa > 1u) {  // too many for one pass: pixel by pixel (<= one bin per value)
+                            single = true;
+                            xe = xa + 1u;
+                            continue;
+                        }
+                        Ea = nact;
+                        clean = !__any_sync(kFull, dirty);
+                        valid_until = clean ? __reduce_min_sync(kFull, vmin) : xe;
+                        if (single) valid_until = xe;
+                        pk_n = 0u;
+                        if (Ea >= 1u && Ea <= 16u) {
+                            pk_n = 32u / Ea;
+                            pk_slot = lane / Ea;
+                            pk_entry = lane - pk_slot * Ea;
+                            const uint2 rec = act[pk_entry];
+                            rx[0] = rec.x;
+                            ry[0] = pk_slot < pk_n ? rec.y : 0xFFFFu;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < KE; k++) {
+                                const uint32_t idx = k * 32 + lane;
+                                uint2 rec = make_uint2(0u, 0xFFFFu);
+                                if (idx < Ea) rec = act[idx];
+                                rx[k] = rec.x;
+                                ry[k] = rec.y;
+                            }
+                        }
+                    }
+                    // ---- emit the pixels [xa, xe) ----
+                    const uint8_t* sp = sb + (size_t)(xa + two_r - cb) * SS;  // window counts of pixel xa
+                    if (pk_n) {
+                        const uint32_t xb = ry[0] & 0xFFFFu, xd = ry[0] >> 16, cid2 = (rx[0] & 0xFFFFu) * 2u, itm = rx[0] >> 16;
+                        for (uint32_t xp = xa; xp < xe; xp += pk_n) {
+                            const uint32_t x = xp + pk_slot;
+                            const bool valid = pk_slot < pk_n && x < xe;
+                            const bool alive = valid && xb <= x && x < xd;
+                            const unsigned bm = __ballot_sync(kFull, alive);
+                            const uint32_t pos = (uint32_t)__popc(bm & lanemask_lt());
+                            if (alive) {
+                                const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (size_t)(x - xa) * SS + cid2);
+                                dst[pos] = make_uint2(itm, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
+                            }
+                            if (valid && pk_entry == 0u) hso_row[x] = off + pos;
+                            const uint32_t nb = (uint32_t)__popc(bm);
+                            dst += nb;
+                            off += nb;
+                        }
+                    } else if (clean) {
+#pragma unroll 4
+                        for (uint32_t x = xa; x < xe; x++) {
+#pragma unroll
+                            for (int k = 0; k < KE; k++) {
+                                if ((uint32_t)(k * 32) < Ea) {
+                                    const uint32_t idx = k * 32 + lane;
+                                    if (idx < Ea) {
+                                        const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (rx[k] & 0xFFFFu) * 2u);
+                                        dst[idx] = make_uint2(rx[k] >> 16, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
+                                    }
+                                }
+                            }
+                            if (lane == 0u) hso_row[x] = off;
+                            dst += Ea;
+                            off += Ea;
+                            sp += SS;
+                        }
+                    } else {
+                        for (uint32_t x = xa; x < xe; x++) {
+                            uint32_t at = 0u;
+#pragma unroll
+                            for (int k = 0; k < KE; k++) {
+                                if ((uint32_t)(k * 32) < Ea) {
+                                    const uint32_t xb = ry[k] & 0xFFFFu, xd = ry[k] >> 16;
+                                    const bool alive = xb <= x && x < xd;
+                                    const unsigned bm = __ballot_sync(kFull, alive);
+                                    if (alive) {
+                                        const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (rx[k] & 0xFFFFu) * 2u);
+                                        dst[at + (uint32_t)__popc(bm & lanemask_lt())] =
+                                            make_uint2(rx[k] >> 16, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
+                                    }
+                                    at += (uint32_t)__popc(bm);
+                                }
+                            }
+                            if (lane == 0u) hso_row[x] = off;
+                            dst += at;
+                            off += at;
+                            sp += SS;
+                        }
+                    }
+                    xa = xe;
+                    xe = single ? min(xa + 1u, xe0) : xe0;
+                }
+            }
+        } else {
+            const uint32_t adv = ce - cb;
+            in_slot += adv;
+            if (in_slot >= R) in_slot -= R;
+            out_slot += adv;
+            if (out_slot >= R) out_slot -= R;
+        }
+        __syncwarp();  // the batch's window counts and the ring columns it read are free again
+        if (b + stages < n_batches && lane == 0u) mbar_arrive(&empty_bar[s]);
+    }
+}
+
+}  // namespace shf

@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(kEventWarps * 32)
 // ------------------------------------------------------------------------------------------------------------------
 // emit: producers as in march_kernel (vertical window counts into a shared-memory ring), consumers = one warp per row
 // ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + 16u; }
+__host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 64u * (uint32_t)K; }
+
 // K bytes of one count vector (compact ids lane*K .. lane*K+K-1) widened to 16-bit pairs
 template <int K>
 __device__ __forceinline__ void load_counts(const uint8_t* p, uint32_t (&v)[(K + 1) / 2]) {
@@ -247,12 +250,49 @@ __device__ __forceinline__ void store_sums(uint8_t* p, const uint32_t (&v)[(K + 
     }
 }
 
+// n columns of the dense horizontal slide: srun += counts(column c) - counts(column c - span); the window counts of a
+// pixel (c >= 2r) go to the staging rows. OUT: the leaving column exists; ST: store.
+template <int K, bool OUT, bool ST>
+__device__ __forceinline__ void slide_cols(const uint8_t* pin, const uint8_t* pout, uint8_t* ps, uint32_t n,
+                                           uint32_t (&srun)[(K + 1) / 2]) {
+    constexpr int CS = 32 * K, SR = (K + 1) / 2;
+    constexpr uint32_t SS = emit_sbuf_stride(K);
+    while (n >= 4u) {
+        uint32_t a[4][SR], o[4][SR];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            load_counts<K>(pin + j * CS, a[j]);
+            if (OUT) load_counts<K>(pout + j * CS, o[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int i = 0; i < SR; i++) srun[i] = OUT ? srun[i] + a[j][i] - o[j][i] : srun[i] + a[j][i];
+            if (ST) store_sums<K>(ps + j * SS, srun);
+        }
+        pin += 4 * CS;
+        pout += 4 * CS;
+        ps += 4 * SS;
+        n -= 4u;
+    }
+    while (n) {
+        uint32_t a[SR], o[SR];
+        load_counts<K>(pin, a);
+        if (OUT) load_counts<K>(pout, o);
+#pragma unroll
+        for (int i = 0; i < SR; i++) srun[i] = OUT ? srun[i] + a[i] - o[i] : srun[i] + a[i];
+        if (ST) store_sums<K>(ps, srun);
+        pin += CS;
+        pout += CS;
+        ps += SS;
+        n--;
+    }
+}
+
 // shared memory of an emit CTA:
 //   cring[TY][R][32K]  u8   vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
 //   sbuf[TY][16][SS]   u16  horizontal window counts of the batch being emitted, SS = 64K + 16 bytes per pixel
 //   act[TY][64K]       8 B  the events overlapping the pixels being emitted, in list order
-__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + 16u; }
-__host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 64u * (uint32_t)K; }
 
 template <int K>
 __global__ void __launch_bounds__(640, 1)
@@ -365,37 +405,24 @@ __global__ void __launch_bounds__(640, 1)
         mbar_wait(&full_bar[s], (b / stages) & 1u);
         if (row_active) {
             // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
-            {
-                const uint8_t* pin = crow + (size_t)in_slot * CS + lane * K;
-                const uint8_t* pout = crow + (size_t)out_slot * CS + lane * K;
-                uint32_t si = in_slot, so = out_slot;
-                uint8_t* ps = sb + lane * (2 * K);
-                for (uint32_t c = cb; c < ce; c++) {
-                    uint32_t a[SR];
-                    load_counts<K>(pin, a);
-#pragma unroll
-                    for (int i = 0; i < SR; i++) srun[i] += a[i];
-                    if (c >= span) {
-                        uint32_t o[SR];
-                        load_counts<K>(pout, o);
-#pragma unroll
-                        for (int i = 0; i < SR; i++) srun[i] -= o[i];
-                    }
-                    if (c >= two_r) store_sums<K>(ps, srun);
-                    ps += SS;
-                    pin += CS;
-                    pout += CS;
-                    if (++si == R) {
-                        si = 0u;
-                        pin = crow + lane * K;
-                    }
-                    if (++so == R) {
-                        so = 0u;
-                        pout = crow + lane * K;
-                    }
-                }
-                in_slot = si;
-                out_slot = so;
+            for (uint32_t c = cb; c < ce;) {
+                // a segment: no ring wrap, the leaving column exists or not, pixels are due or not
+                const bool has_out = c >= span, st = c >= two_r;
+                uint32_t seg_end = min(ce, c + (R - in_slot));
+                seg_end = has_out ? min(seg_end, c + (R - out_slot)) : min(seg_end, span);
+                if (!st) seg_end = min(seg_end, two_r);
+                const uint32_t n = seg_end - c;
+                const uint8_t* pin = crow + in_slot * CS + lane * K;
+                const uint8_t* pout = crow + out_slot * CS + lane * K;
+                uint8_t* ps = sb + (c - cb) * SS + lane * (2 * K);
+                if (has_out) slide_cols<K, true, true>(pin, pout, ps, n, srun);
+                else if (st) slide_cols<K, false, true>(pin, pout, ps, n, srun);
+                else slide_cols<K, false, false>(pin, pout, ps, n, srun);
+                in_slot += n;
+                if (in_slot >= R) in_slot -= R;
+                out_slot += n;
+                if (out_slot >= R) out_slot -= R;
+                c = seg_end;
             }
             __syncwarp();
             // ---- the pixels of this batch: x = c - 2r ----
@@ -462,21 +489,30 @@ __global__ void __launch_bounds__(640, 1)
                     // ---- emit the pixels [xa, xe) ----
                     const uint8_t* sp = sb + (size_t)(xa + two_r - cb) * SS;  // window counts of pixel xa
                     if (pk_n) {
-                        const uint32_t xb = ry[0] & 0xFFFFu, xd = ry[0] >> 16, cid2 = (rx[0] & 0xFFFFu) * 2u, itm = rx[0] >> 16;
+                        // lane = slot * Ea + entry: pk_n pixels per pass; positions by one ballot + popc
+                        const uint32_t xb = ry[0] & 0xFFFFu, lim = min(ry[0] >> 16, xe), itm = rx[0] >> 16;
+                        const uint32_t len = lim > xb ? lim - xb : 0u;             // alive <=> (x - xb) < len
+                        const uint32_t hlim = (pk_entry == 0u && pk_slot < pk_n) ? xe : 0u;  // this lane stores the offset of x
+                        uint32_t x = xa + pk_slot;
+                        uint32_t sa = smem_addr(sp) + pk_slot * SS + (rx[0] & 0xFFFFu) * 2u;
+                        const uint32_t sa_step = pk_n * SS;
+                        uint32_t* hp = hso_row + x;
                         for (uint32_t xp = xa; xp < xe; xp += pk_n) {
-                            const uint32_t x = xp + pk_slot;
-                            const bool valid = pk_slot < pk_n && x < xe;
-                            const bool alive = valid && xb <= x && x < xd;
+                            const bool alive = x - xb < len;
                             const unsigned bm = __ballot_sync(kFull, alive);
                             const uint32_t pos = (uint32_t)__popc(bm & lanemask_lt());
                             if (alive) {
-                                const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (size_t)(x - xa) * SS + cid2);
+                                uint32_t cnt;
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cnt) : "r"(sa));
                                 dst[pos] = make_uint2(itm, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
                             }
-                            if (valid && pk_entry == 0u) hso_row[x] = off + pos;
+                            if (x < hlim) *hp = off + pos;
                             const uint32_t nb = (uint32_t)__popc(bm);
                             dst += nb;
                             off += nb;
+                            x += pk_n;
+                            sa += sa_step;
+                            hp += pk_n;
                         }
                     } else if (clean) {
 #pragma unroll 4

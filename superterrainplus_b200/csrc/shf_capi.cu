@@ -151,7 +151,8 @@ size_t march_smem(uint32_t ty, uint32_t R, int K) {
 }
 
 size_t emit_smem(uint32_t ty, uint32_t R, int K) {
-    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K) + (size_t)ty * shf::emit_act_cap(K) * 8 + 128;
+    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K) + (size_t)ty * shf::emit_act_cap(K) * 8 + 128 +
+           4 * 1024;  // barriers + the producers' sample scratch (<= 1 KB per producer warp)
 }
 
 constexpr uint32_t kLegacyMarch = 4u;  // SHF_DEBUG_FLAGS bit: the list-maintaining march_kernel instead of events + emit
@@ -273,7 +274,7 @@ int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) 
 // scratch every path needs + the compact-id map and the dictionary
 int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
     const size_t cells = (size_t)g.n_chunks * g.PH * g.P;
-    SHF_CUDA(b->cmap.ensure(cells * 2));
+    SHF_CUDA(b->cmap.ensure(cells * 2 + 64));  // producers read whole 16/32-byte row segments
     SHF_CUDA(b->vstart.ensure(cells * 2));
     SHF_CUDA(b->dict.ensure((size_t)g.n_chunks * g.Bpad * 2));
     SHF_CUDA(b->rowtotal.ensure((size_t)g.n_chunks * g.H * 4));

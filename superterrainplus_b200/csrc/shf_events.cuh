@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(kEventWarps * 32)
 // ------------------------------------------------------------------------------------------------------------------
 // emit: producers as in march_kernel (vertical window counts into a shared-memory ring), consumers = one warp per row
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + 16u; }
-__host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 64u * (uint32_t)K; }
+__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + (K <= 2 ? 4u : 2u * (uint32_t)K); }
+__host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 32u * (uint32_t)K + 32u; }
 
 // K bytes of one count vector (compact ids lane*K .. lane*K+K-1) widened to 16-bit pairs
 template <int K>
@@ -291,8 +291,8 @@ __device__ __forceinline__ void slide_cols(const uint8_t* pin, const uint8_t* po
 
 // shared memory of an emit CTA:
 //   cring[TY][R][32K]  u8   vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
-//   sbuf[TY][16][SS]   u16  horizontal window counts of the batch being emitted, SS = 64K + 16 bytes per pixel
-//   act[TY][64K]       8 B  the events overlapping the pixels being emitted, in list order
+//   sbuf[TY][16][SS]   u16  horizontal window counts of the batch being emitted, SS = 64K + pad bytes per pixel
+//   act[TY][32K+32]    8 B  the events overlapping the pixels being emitted, in list order
 
 template <int K>
 __global__ void __launch_bounds__(640, 1)
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(640, 1)
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int CS = 32 * K;
     constexpr int NB = kMarchNB;
-    constexpr int KE = 2 * K;                      // register sets of the active list
+    constexpr int KE = K + 1;                      // register sets of the active list
     constexpr uint32_t SS = emit_sbuf_stride(K);
     constexpr uint32_t ACAP = emit_act_cap(K);
     constexpr int SR = (K + 1) / 2;
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(640, 1)
     uint2* act_all = reinterpret_cast<uint2*>(sbuf_all + (size_t)TY * NB * SS);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(act_all + (size_t)TY * ACAP);
     uint64_t* empty_bar = full_bar + 8;
+    uint8_t* pscr_all = reinterpret_cast<uint8_t*>(empty_bar + 8);  // [producers][2][CPP][16] u16
     if (threadIdx.x < stages) {
         mbar_init(&full_bar[threadIdx.x], (uint32_t)(NB / (32 / (2 * K))));
         mbar_init(&empty_bar[threadIdx.x], TY);
@@ -326,38 +327,79 @@ __global__ void __launch_bounds__(640, 1)
     const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
 
     if (warp >= TY) {
-        // =============================== producer warps (see march_kernel) ===============================
-        constexpr int LPC = 2 * K;
-        constexpr int CPP = 32 / LPC;
-        constexpr int PPB = NB / CPP;
+        // =============================== producer warps ===============================
+        // Work item t = (batch b, pass q): CPP columns x the tile's rows. The samples entering / leaving the vertical
+        // window (rows y0+i+span and y0+i) are fetched as one row segment per lane (lanes 0-15 entering, 16-31
+        // leaving), a whole item ahead of their use, and handed to the column lanes through a transposed scratch.
+        constexpr int LPC = 2 * K;       // lanes per column, 16 bytes of counters each
+        constexpr int CPP = 32 / LPC;    // columns per pass
+        constexpr int PPB = NB / CPP;    // passes per batch
+        constexpr int SW = CPP / 2;      // 32-bit words of one row segment
         const uint32_t part = lane % LPC, colq = lane / LPC;
         const uint32_t tile_rows = min(TY, g.H - y0);
         const uint32_t bit0 = part * 128u;
-        for (uint32_t t = warp - TY; t < n_batches * PPB; t += NP) {
+        const uint32_t half = lane >> 4, lrow = lane & 15u;
+        uint16_t* scr = reinterpret_cast<uint16_t*>(pscr_all) + (size_t)(warp - TY) * (2 * CPP * 16);
+        const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.P;
+        const uint8_t* base_tile = base + ((size_t)n_chunk * g.T + tile) * PW * CS + part * 16u;
+        const uint32_t n_items = n_batches * PPB;
+        uint32_t seg_n[SW];
+        uint4 v_n = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch = [&](uint32_t t) {
+            const uint32_t c0 = (t / PPB) * NB + (t % PPB) * CPP;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(seg_row + c0);
+            if (SW == 8) {
+                const uint4 a = reinterpret_cast<const uint4*>(src)[0], b2 = reinterpret_cast<const uint4*>(src)[1];
+                seg_n[0] = a.x, seg_n[1] = a.y, seg_n[2] = a.z, seg_n[3] = a.w;
+                seg_n[4 % SW] = b2.x, seg_n[5 % SW] = b2.y, seg_n[6 % SW] = b2.z, seg_n[7 % SW] = b2.w;
+            } else if (SW == 4) {
+                const uint4 a = reinterpret_cast<const uint4*>(src)[0];
+                seg_n[0] = a.x, seg_n[1 % SW] = a.y, seg_n[2 % SW] = a.z, seg_n[3 % SW] = a.w;
+            } else if (SW == 2) {
+                const uint2 a = reinterpret_cast<const uint2*>(src)[0];
+                seg_n[0] = a.x, seg_n[1 % SW] = a.y;
+            } else {
+                seg_n[0] = src[0];
+            }
+            const uint32_t c = min(c0 + colq, PW - 1u);
+            v_n = *reinterpret_cast<const uint4*>(base_tile + (size_t)c * CS);
+        };
+        uint32_t t = warp - TY;
+        if (t < n_items) fetch(t);
+        for (; t < n_items; t += NP) {
             const uint32_t b = t / PPB, pass = t % PPB;
             const uint32_t s = b % stages, cb = b * NB;
-            const uint32_t slot0 = cb % R;
             const uint32_t cu = pass * CPP + colq;
             const bool live = cb + cu < PW;
-            const uint32_t c = live ? cb + cu : PW - 1u;
-            uint32_t slot = slot0 + cu;
+            uint32_t slot = cb % R + cu;
             if (slot >= R) slot -= R;
-            uint4 v = *reinterpret_cast<const uint4*>(base + (((size_t)n_chunk * g.T + tile) * PW + c) * CS + part * 16u);
-            uint32_t sa[16], so[16];
+            uint4 v = v_n;
+            // transposed scratch: scr[half][column][row]
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t pi = min(y0 + i + span, g.PH - 1u), po = min(y0 + i, g.PH - 1u);
-                sa[i] = cm[(size_t)pi * g.P + c];
-                so[i] = cm[(size_t)po * g.P + c];
+            for (int j = 0; j < CPP; j++)
+                scr[(half * CPP + j) * 16 + lrow] = (uint16_t)(seg_n[j / 2] >> (16 * (j & 1)));
+            if (t + NP < n_items) fetch(t + NP);
+            __syncwarp();
+            uint32_t wa[8], wo[8];
+            {
+                const uint4* pa = reinterpret_cast<const uint4*>(scr + colq * 16);
+                const uint4* po = reinterpret_cast<const uint4*>(scr + (CPP + colq) * 16);
+                const uint4 a0 = pa[0], a1 = pa[1], o0 = po[0], o1 = po[1];
+                wa[0] = a0.x, wa[1] = a0.y, wa[2] = a0.z, wa[3] = a0.w, wa[4] = a1.x, wa[5] = a1.y, wa[6] = a1.z, wa[7] = a1.w;
+                wo[0] = o0.x, wo[1] = o0.y, wo[2] = o0.z, wo[3] = o0.w, wo[4] = o1.x, wo[5] = o1.y, wo[6] = o1.z, wo[7] = o1.w;
             }
-            if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);
+            if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);  // batch b - stages is consumed
             uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 if ((uint32_t)i < tile_rows) {
                     if (live) *reinterpret_cast<uint4*>(out) = v;
                     out += (size_t)R * CS;
-                    const uint32_t ba = sa[i] * 8u - bit0, bo = so[i] * 8u - bit0;
+                    // counter of compact id a sits at bit 8a of the column vector; a shift by >= 32 (or "negative",
+                    // i.e. huge) yields 0 with PTX shl, so every word only sees its own counters
+                    const uint32_t sa = (i & 1) ? wa[i / 2] >> 16 : wa[i / 2] & 0xFFFFu;
+                    const uint32_t so = (i & 1) ? wo[i / 2] >> 16 : wo[i / 2] & 0xFFFFu;
+                    const uint32_t ba = sa * 8u - bit0, bo = so * 8u - bit0;
                     v.x += shl_clamp(1u, ba) - shl_clamp(1u, bo);
                     v.y += shl_clamp(1u, ba - 32u) - shl_clamp(1u, bo - 32u);
                     v.z += shl_clamp(1u, ba - 64u) - shl_clamp(1u, bo - 64u);

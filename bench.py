@@ -10,7 +10,7 @@ radius 64, 64 biomes; biome ids iid uniform like the reference's own benchmark (
 path, weak scaling; `value` = pixels of all ranks / max-over-ranks device time.
 
 Printed keys beyond the base contract:
-  roofline      the emitting march kernel: algorithmic bytes of the step / its CUDA-event duration vs the measured HBM peak
+  roofline      the emitting kernel (emit_kernel<K>): algorithmic bytes of the step / its CUDA-event duration vs the measured HBM peak
   phases_ms     median CUDA-event time of every kernel phase of a step
   cpu_baseline  the reference's own filter (oracle/_ref, else the C restatement) timed on this box's host cores on a
                 bounded sample of the same chunks (N=1 only)
@@ -331,7 +331,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     emit_ms = phases_ms["march_emit"]
     achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "march_kernel<K,emit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "emit_kernel<K>" if plan["k_sets"] else "march_generic_kernel<emit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
                 "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}

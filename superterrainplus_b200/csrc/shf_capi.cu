@@ -146,8 +146,11 @@ namespace {
 
 using shf::Geo;
 
-size_t march_smem(uint32_t ty, uint32_t R, int K) {
-    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * K * 4 + (size_t)ty * 2 * 32 * K * 4 + 32 * K * 2 + 128;
+// CTAs per chunk of the row-streaming kernels (dictionary, remap): about 8 CTAs per SM over the whole batch; every CTA
+// carries a fixed cost (zeroing / loading 8-16 KB of tables), so large batches use few CTAs per chunk
+uint32_t shf_rows_grid(uint32_t PH, uint32_t n_chunks) {
+    const uint32_t want = (8u * 148u + n_chunks - 1u) / n_chunks;
+    return std::max(1u, std::min(std::min(want, PH), 256u));
 }
 
 size_t emit_smem(uint32_t ty, uint32_t R, int K) {
@@ -155,7 +158,6 @@ size_t emit_smem(uint32_t ty, uint32_t R, int K) {
            4 * 1024;  // barriers + the producers' sample scratch (<= 1 KB per producer warp)
 }
 
-constexpr uint32_t kLegacyMarch = 4u;  // SHF_DEBUG_FLAGS bit: the list-maintaining march_kernel instead of events + emit
 
 template <int K>
 int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
@@ -185,67 +187,22 @@ template <int K>
 int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
         const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
-        const size_t vsmem = (size_t)shf::kVscanThreads * (5 * 32 * K + 4);
+        const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K;
         SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
         shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(),
                                                                      b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));
-        if (!(g.flags & kLegacyMarch)) return launch_events<K>(b, g, s);
-        // a warp stages `rows` rows of masks plus their suffix ORs; lanes own (row, block of 2r+1 columns, mask word)
-        shf::RowcountPlan rp{};
-        rp.nblk = (g.PW + g.span - 1u) / g.span;
-        const uint32_t chains = rp.nblk * K;
-        rp.rows = std::max(1u, std::min(32u / chains, g.H));
-        rp.stride = g.PW * K;
-        if (rp.rows > 1u) rp.stride += (32u + 32u / rp.rows - rp.stride % 32u) % 32u;  // rows land on different banks
-        const size_t per_warp = ((size_t)2 * rp.rows * rp.stride + 32u) * 4;
-        uint32_t warps = 2;
-        while (warps > 1 && warps * per_warp > 100 * 1024) warps >>= 1;
-        while (rp.rows > 1u && warps * (((size_t)2 * rp.rows * rp.stride + 32u) * 4) > 200 * 1024) rp.rows--;
-        const size_t rsmem = warps * (((size_t)2 * rp.rows * rp.stride + 32u) * 4);
-        if (rsmem > 200 * 1024) return fail(SHF_ERR_UNSUPPORTED, "row masks fit shared memory", "map too wide");
-        SHF_CUDA(cudaFuncSetAttribute(shf::rowcount_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        const uint32_t rows_per_cta = warps * rp.rows;
-        shf::rowcount_kernel<K><<<dim3((g.H + rows_per_cta - 1) / rows_per_cta, g.n_chunks), warps * 32, rsmem, s>>>(
-            g, rp, b->colmask.as<uint32_t>(), b->rowtotal.as<uint32_t>());
-        tls_launches++;
-        SHF_CUDA(cudaGetLastError());
-    } else if (!(g.flags & kLegacyMarch)) {
-        const size_t smem = emit_smem(g.TY, g.R, K);
-        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::emit_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
-            g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
-            b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
-        tls_launches++;
-        SHF_CUDA(cudaGetLastError());
-    } else {
-        Geo gd = g;
-        if (g.flags & 2u) {  // measurement only: cycle counters of the march kernel printed to stderr
-            SHF_CUDA(b->gstate.ensure(64));
-            SHF_CUDA(cudaMemsetAsync(b->gstate.p, 0, 64, s));
-            gd.dbg = b->gstate.as<unsigned long long>();
-        }
-        const size_t smem = march_smem(g.TY, g.R, K);
-        SHF_CUDA(cudaFuncSetAttribute(shf::march_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shf::march_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
-            gd, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
-            b->dict.as<uint16_t>(), 32 * K, b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(),
-            b->hso.as<uint32_t>());
-        tls_launches++;
-        SHF_CUDA(cudaGetLastError());
-        if (gd.dbg) {
-            unsigned long long h[8];
-            SHF_CUDA(cudaMemcpyAsync(h, gd.dbg, sizeof(h), cudaMemcpyDeviceToHost, s));
-            SHF_CUDA(cudaStreamSynchronize(s));
-            const double cw = (double)g.T * g.n_chunks * g.TY, pw = (double)g.T * g.n_chunks * g.producers;
-            fprintf(stderr,
-                    "[shf dbg] per consumer warp: %.0f cycles, waiting for producers %.0f, list changes %.0f cycles in %.1f events; "
-                    "per producer warp: %.0f cycles, waiting for consumers %.0f, producing %.0f\n",
-                    h[0] / cw, h[1] / cw, h[5] / cw, h[6] / cw, h[2] / pw, h[3] / pw, h[4] / pw);
-        }
+        return launch_events<K>(b, g, s);
     }
+    const size_t smem = emit_smem(g.TY, g.R, K);
+    SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shf::emit_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
+        g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+        b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
     return SHF_OK;
 }
 
@@ -282,7 +239,7 @@ int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec
     SHF_CUDA(b->chunktotal.ensure((size_t)(g.n_chunks + 1) * 8));  // + the event counter
     SHF_CUDA(b->chunkbase.ensure((size_t)(g.n_chunks + 1) * 8));
     SHF_CUDA(b->hso.ensure((size_t)g.n_chunks * ((size_t)g.W * g.H + 1u) * 4));
-    const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), g.n_chunks);
+    const dim3 pgrid(shf_rows_grid(g.PH, g.n_chunks), g.n_chunks);
     if (vec8)
         shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
                                                    b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
@@ -421,7 +378,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
     SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
-    const dim3 pgrid(std::min<uint32_t>(g.PH, 64u), n_chunks);
+    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks), n_chunks);
     // 16-byte loads when the halo view allows it
     const bool vec8 = (reinterpret_cast<uintptr_t>(in_dev) % 16u == 0u) && (in_row_stride % 8u == 0u) && (in_chunk_stride % 8u == 0u);
     if (vec8)
@@ -458,7 +415,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             g.stages = (np + ppb - 1u) / ppb + extra;
             g.R = g.span + shf::kMarchNB * g.stages;
         };
-        auto smem_of = [&](uint32_t t) { return (g.flags & kLegacyMarch) ? march_smem(t, g.R, K) : emit_smem(t, g.R, K); };
+        auto smem_of = [&](uint32_t t) { return emit_smem(t, g.R, K); };
         plan(4u, 2u);
         if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
         if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
@@ -479,9 +436,8 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     if (generic) return run_generic(f, b, g, in_dev, vec8, bmax, h_totals, s);
 
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
-    SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * g.PW * K * 4));
-    const bool events = !(g.flags & kLegacyMarch);
-    if (events) {
+    SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * ((g.PW + 31u) / 32u) * 32u * K * 4));  // transposed masks per 32-column block
+    {
         SHF_CUDA(b->rowinfo.ensure((size_t)n_chunks * H * 8));
         SHF_CUDA(b->evpool.ensure((size_t)n_chunks * H * 32u * (K + 1) * 8));
     }
@@ -491,7 +447,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     // ---- vertical scan + bins per row ----
     st = dispatch_chain(K, b, g, s, 0);
     if (st != SHF_OK) return st;
-    st = size_output(b, g, h_totals, s, events);
+    st = size_output(b, g, h_totals, s, true);
     if (st != SHF_OK) return st;
 
     // ---- emitting march ----

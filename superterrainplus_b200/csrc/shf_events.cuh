@@ -8,7 +8,7 @@
 //   * the chain's bin exists for the pixels x with  max(c_b - 2r, 0) <= x <= min(c_l, W - 1)
 //   * a pixel lists the bins of the events alive at x, ordered by birth: (c_b, vertical chain start of the value in
 //     column c_b) -- the second key is the order of the column's own intermediate histogram (SHF.cpp:522-563).
-// events_kernel builds the sorted event list of every row from the per-(row, column) presence masks of vscan_kernel and
+// events_kernel builds the sorted event list of every row from the transposed presence masks of vscan_kernel and
 // totals the bins per row (which replaces a counting march). emit_kernel then needs no sequential list maintenance at
 // all: a pixel's bins are the alive events in list order (warp ballot + popc gives the position), the counts come from
 // a dense per-row horizontal sliding sum kept next to the shared-memory ring of vertical window counts.
@@ -22,16 +22,28 @@ constexpr uint32_t kEventStage = 192;   // events of one row staged in shared me
 constexpr uint32_t kNoEvent = 0xFFFFFFFFu;
 
 // Event record, 8 bytes: x = compact id | sample value << 16, y = first pixel | (last pixel + 1) << 16
-__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
-    // lane i holds row i of a 32x32 bit matrix; afterwards lane i holds column i (bit r = former row r, bit i)
-    uint32_t m = 0x0000FFFFu;
+// 32-column mask blocks staged per cp.async group (two groups = 4 KB in flight per warp)
+__host__ __device__ constexpr int event_group(int K) { return K <= 2 ? 8 : K == 4 ? 4 : 2; }
+
+// The transposed masks of `event_group(K)` blocks of 32 columns, copied asynchronously into shared memory: the walk
+// below consumes a block every few dozen instructions, so without many bytes in flight per warp it would be bound by
+// DRAM latency.
+template <int K>
+__device__ __forceinline__ void stage_masks(uint32_t* sdst, const uint32_t* __restrict__ tmask_row, uint32_t w0,
+                                            uint32_t n_words, uint32_t lane) {
+    constexpr int kEventGroup = event_group(K);
 #pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-        const uint32_t other = __shfl_xor_sync(kFull, x, j);
-        x = (lane & (uint32_t)j) ? ((x & ~m) | ((other >> j) & m)) : ((x & m) | ((other << j) & ~m));
-        m ^= m << (j >> 1);
+    for (int i = 0; i < kEventGroup; i++) {
+        if (w0 + (uint32_t)i < n_words) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t* src = tmask_row + ((size_t)(w0 + i) * K + k) * 32u + lane;
+                const uint32_t dst = smem_addr(sdst + (i * K + k) * 32 + lane);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
     }
-    return x;
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // One pass over the row's presence masks. Writes at most `cap` records to `dst` (shared staging or the row's pool
@@ -39,8 +51,8 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
 template <int K>
 __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t lane, const uint32_t* __restrict__ cmask_row,
                                              const uint16_t* __restrict__ cm, const uint16_t* __restrict__ vs,
-                                             const uint32_t (&item)[K], uint16_t* tab, uint2* dst, uint32_t cap,
-                                             uint32_t& bins_total) {
+                                             const uint32_t (&item)[K], uint16_t* tab, uint32_t* mstage, uint2* dst,
+                                             uint32_t cap, uint32_t& bins_total) {
     const uint32_t PW = g.PW, span = g.span, two_r = 2u * g.r, W = g.W;
     int32_t last[K];
     uint32_t open[K], openxb[K];
@@ -52,21 +64,25 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
     }
     uint32_t E = 0u;
     const uint32_t n_words = (PW + 31u) / 32u;
-    uint32_t mnext[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) mnext[k] = lane < PW ? cmask_row[(size_t)lane * K + k] : 0u;
+    constexpr int kEventGroup = event_group(K);
+    constexpr uint32_t GW = kEventGroup * 32 * K;  // words of one staged group
+    __syncwarp();
+    stage_masks<K>(mstage, cmask_row, 0u, n_words, lane);
+    stage_masks<K>(mstage + GW, cmask_row, (uint32_t)kEventGroup, n_words, lane);
     for (uint32_t w = 0u; w < n_words; w++) {
         const uint32_t c0 = w * 32u;
-        uint32_t rem[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) rem[k] = mnext[k];
-        {
-            const uint32_t cn = c0 + 32u + lane;
-#pragma unroll
-            for (int k = 0; k < K; k++) mnext[k] = cn < PW ? cmask_row[(size_t)cn * K + k] : 0u;
+        const uint32_t gi = w / kEventGroup, wi = w % kEventGroup;
+        if (wi == 0u) {
+            if (w) {  // the buffer of the group just finished is free: stage the group after the next into it
+                __syncwarp();
+                stage_masks<K>(mstage + ((gi + 1u) & 1u) * GW, cmask_row, (gi + 1u) * kEventGroup, n_words, lane);
+            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
         }
+        uint32_t rem[K];  // lane = compact id 32k + lane, bit j = column c0 + j
 #pragma unroll
-        for (int k = 0; k < K; k++) rem[k] = transpose32(rem[k], lane);  // lane = compact id 32k + lane, bit j = column c0 + j
+        for (int k = 0; k < K; k++) rem[k] = mstage[(gi & 1u) * GW + (wi * K + k) * 32u + lane];
         for (;;) {
             // every lane advances to its next birth inside this word
             uint32_t bj[K], jmin = 32u;
@@ -109,10 +125,20 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
             if (gsz > 1u) {
                 // order them by the start row of their vertical chain: every cell of the column's window publishes the
                 // chain start of its value (all cells of one value inside a window agree)
-                for (uint32_t o = lane; o < span; o += 32u) {
-                    const size_t at = (size_t)(y + o) * g.P + c;
-                    tab[cm[at]] = vs[at];
+                // (2r+1 <= 255 on this path: 8 cells per lane at most; all loads go out before the first store)
+                uint32_t cid[8], vst[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t o = lane + 32u * (uint32_t)i;
+                    if (o < span) {
+                        const size_t at = (size_t)(y + o) * g.P + c;
+                        cid[i] = cm[at];
+                        vst[i] = vs[at];
+                    }
                 }
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (lane + 32u * (uint32_t)i < span) tab[cid[i]] = (uint16_t)vst[i];
                 __syncwarp();
                 uint32_t vk[K];
 #pragma unroll
@@ -155,6 +181,7 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
             E += gsz;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < K; k++) {
         if (open[k] != kNoEvent) {
@@ -169,19 +196,21 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
 // rowinfo(n, y) = (first record of the row in the pool, number of records). counter[0] = records handed out so far;
 // a row whose slot would end beyond `pool_cap` writes nothing (the host grows the pool and runs the kernel again).
 template <int K>
-__global__ void __launch_bounds__(kEventWarps * 32)
+__global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K == 4 ? 4 : 3)
     events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint16_t* __restrict__ cmap,
                   const uint16_t* __restrict__ vstart, const uint16_t* __restrict__ dict, uint32_t dict_stride,
                   uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
                   uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal) {
     __shared__ uint2 stage_all[kEventWarps][kEventStage];
     __shared__ uint16_t tab_all[kEventWarps][32 * K];
+    __shared__ __align__(16) uint32_t mstage_all[kEventWarps][2 * event_group(K) * 32 * K];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n = blockIdx.y, y = blockIdx.x * kEventWarps + warp;
     if (y >= g.H) return;
     uint2* stage = stage_all[warp];
     uint16_t* tab = tab_all[warp];
-    const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * g.PW * K;
+    uint32_t* mstage = mstage_all[warp];
+    const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * ((g.PW + 31u) / 32u) * 32u * K;  // transposed masks
     const uint16_t* cm = cmap + (size_t)n * g.PH * g.P;
     const uint16_t* vs = vstart + (size_t)n * g.PH * g.P;
     uint32_t item[K];
@@ -191,7 +220,7 @@ __global__ void __launch_bounds__(kEventWarps * 32)
         item[k] = id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
     }
     uint32_t bins = 0u;
-    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, stage, kEventStage, bins);
+    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, mstage, stage, kEventStage, bins);
     bins = __reduce_add_sync(kFull, bins);
     unsigned long long first = 0ull;
     if (lane == 0u) first = atomicAdd(counter, (unsigned long long)E);
@@ -206,7 +235,7 @@ __global__ void __launch_bounds__(kEventWarps * 32)
         for (uint32_t i = lane; i < E; i += 32u) pool[first + i] = stage[i];
     } else {
         uint32_t again = 0u;
-        (void)walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, pool + first, E, again);
+        (void)walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, mstage, pool + first, E, again);
     }
 }
 

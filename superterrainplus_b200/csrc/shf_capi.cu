@@ -106,7 +106,7 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
-        bins, hso, gstate, evpool, rowinfo;
+        bins, hso, gstate, evpool, rowinfo, cvt;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
     uint32_t n_chunks = 0, last_w = 0, last_h = 0;
@@ -132,7 +132,7 @@ struct shf_buffer {
         ev_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
                        &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
-                       &evpool, &rowinfo};
+                       &evpool, &rowinfo, &cvt};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -164,7 +164,7 @@ int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
     unsigned long long* counter = b->chunktotal.as<unsigned long long>() + g.n_chunks;
     SHF_CUDA(cudaMemsetAsync(counter, 0, 8, s));
     shf::events_kernel<K><<<dim3((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks), shf::kEventWarps * 32, 0, s>>>(
-        g, b->colmask.as<uint32_t>(), b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(), b->dict.as<uint16_t>(), 32 * K,
+        g, b->colmask.as<uint32_t>(), b->cvt.as<uint32_t>(), b->dict.as<uint16_t>(), 32 * K,
         b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), counter, b->rowinfo.as<uint2>(),
         b->rowtotal.as<uint32_t>());
     tls_launches++;
@@ -187,9 +187,9 @@ template <int K>
 int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
         const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
-        const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K;
+        const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K + 32 * 33 * 4;
         SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-        shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->vstart.as<uint16_t>(),
+        shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
                                                                      b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
@@ -232,7 +232,6 @@ int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) 
 int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
     const size_t cells = (size_t)g.n_chunks * g.PH * g.P;
     SHF_CUDA(b->cmap.ensure(cells * 2 + 64));  // producers read whole 16/32-byte row segments
-    SHF_CUDA(b->vstart.ensure(cells * 2));
     SHF_CUDA(b->dict.ensure((size_t)g.n_chunks * g.Bpad * 2));
     SHF_CUDA(b->rowtotal.ensure((size_t)g.n_chunks * g.H * 4));
     SHF_CUDA(b->rowbase.ensure((size_t)g.n_chunks * g.H * 4));
@@ -312,6 +311,7 @@ int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_d
     if (smem > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "per-row tables fit shared memory", "radius x biome count too large for one CTA");
     b->plan_smem = (uint32_t)smem;
+    SHF_CUDA(b->vstart.ensure((size_t)g.n_chunks * g.PH * g.P * 2));
     int st = prepare_common(b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
     // vertical chain starts; per-(biome, column) state for a sub-batch of chunks at a time (<= 1 GiB of scratch)
@@ -438,6 +438,9 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
     SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * ((g.PW + 31u) / 32u) * 32u * K * 4));  // transposed masks per 32-column block
     {
+        g.cv_pad = (32u - g.span % 32u) % 32u;
+        g.cv_pitch = (g.PH + g.cv_pad + 31u) & ~31u;
+        SHF_CUDA(b->cvt.ensure((size_t)n_chunks * g.PW * g.cv_pitch * 4));
         SHF_CUDA(b->rowinfo.ensure((size_t)n_chunks * H * 8));
         SHF_CUDA(b->evpool.ensure((size_t)n_chunks * H * 32u * (K + 1) * 8));
     }

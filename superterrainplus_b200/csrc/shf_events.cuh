@@ -50,8 +50,7 @@ __device__ __forceinline__ void stage_masks(uint32_t* sdst, const uint32_t* __re
 // slot); returns the number of events and adds the row's bins to `bins_total` (per-lane partial sums).
 template <int K>
 __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t lane, const uint32_t* __restrict__ cmask_row,
-                                             const uint16_t* __restrict__ cm, const uint16_t* __restrict__ vs,
-                                             const uint32_t (&item)[K], uint16_t* tab, uint32_t* mstage, uint2* dst,
+                                             const uint32_t* __restrict__ cv, const uint32_t (&item)[K], uint16_t* tab, uint32_t* mstage, uint2* dst,
                                              uint32_t cap, uint32_t& bins_total) {
     const uint32_t PW = g.PW, span = g.span, two_r = 2u * g.r, W = g.W;
     int32_t last[K];
@@ -126,19 +125,16 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
                 // order them by the start row of their vertical chain: every cell of the column's window publishes the
                 // chain start of its value (all cells of one value inside a window agree)
                 // (2r+1 <= 255 on this path: 8 cells per lane at most; all loads go out before the first store)
-                uint32_t cid[8], vst[8];
+                uint32_t cell[8];
+                const uint32_t* colw = cv + (size_t)c * g.cv_pitch + g.cv_pad + y;  // the column's window, contiguous
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const uint32_t o = lane + 32u * (uint32_t)i;
-                    if (o < span) {
-                        const size_t at = (size_t)(y + o) * g.P + c;
-                        cid[i] = cm[at];
-                        vst[i] = vs[at];
-                    }
+                    if (o < span) cell[i] = colw[o];
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    if (lane + 32u * (uint32_t)i < span) tab[cid[i]] = (uint16_t)vst[i];
+                    if (lane + 32u * (uint32_t)i < span) tab[cell[i] & 0xFFFFu] = (uint16_t)(cell[i] >> 16);
                 __syncwarp();
                 uint32_t vk[K];
 #pragma unroll
@@ -197,8 +193,8 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
 // a row whose slot would end beyond `pool_cap` writes nothing (the host grows the pool and runs the kernel again).
 template <int K>
 __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K == 4 ? 4 : 3)
-    events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint16_t* __restrict__ cmap,
-                  const uint16_t* __restrict__ vstart, const uint16_t* __restrict__ dict, uint32_t dict_stride,
+    events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint32_t* __restrict__ cvt,
+                  const uint16_t* __restrict__ dict, uint32_t dict_stride,
                   uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
                   uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal) {
     __shared__ uint2 stage_all[kEventWarps][kEventStage];
@@ -211,8 +207,7 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     uint16_t* tab = tab_all[warp];
     uint32_t* mstage = mstage_all[warp];
     const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * ((g.PW + 31u) / 32u) * 32u * K;  // transposed masks
-    const uint16_t* cm = cmap + (size_t)n * g.PH * g.P;
-    const uint16_t* vs = vstart + (size_t)n * g.PH * g.P;
+    const uint32_t* cv = cvt + (size_t)n * g.PW * g.cv_pitch;
     uint32_t item[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -220,7 +215,7 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
         item[k] = id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
     }
     uint32_t bins = 0u;
-    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, mstage, stage, kEventStage, bins);
+    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cv, item, tab, mstage, stage, kEventStage, bins);
     bins = __reduce_add_sync(kFull, bins);
     unsigned long long first = 0ull;
     if (lane == 0u) first = atomicAdd(counter, (unsigned long long)E);
@@ -235,7 +230,7 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
         for (uint32_t i = lane; i < E; i += 32u) pool[first + i] = stage[i];
     } else {
         uint32_t again = 0u;
-        (void)walk_row<K>(g, y, lane, cmask_row, cm, vs, item, tab, mstage, pool + first, E, again);
+        (void)walk_row<K>(g, y, lane, cmask_row, cv, item, tab, mstage, pool + first, E, again);
     }
 }
 

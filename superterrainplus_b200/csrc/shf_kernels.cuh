@@ -41,6 +41,7 @@ struct Geo {
     uint32_t stages;               // batches the march producers may run ahead of the consumers (2..6)
     uint32_t producers;            // producer warps of the march kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
+    uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
     uint32_t flags;                // bit 0: do not use the packed short-list path (A/B measurements)
     unsigned long long* dbg;       // measurement only: cycle counters of the march kernel, or null
@@ -217,6 +218,31 @@ __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint3
 // Output per (row y, column block): the presence masks TRANSPOSED, tmask(n, y, block)[id] = 32 bits, bit j set iff
 // compact id `id` occurs in column 32*block + j, rows [y, y+2r]. They are kept incrementally in shared memory (a count
 // reaching / leaving zero flips one bit with a shared-memory atomic), so events_kernel reads them lane = id as they are.
+// (free functions taking plain values: a noinline member would force the whole state struct into local memory)
+__device__ __noinline__ void vscan_flush(const uint32_t* stg, uint32_t* cv_blk, uint32_t cv_pitch, uint32_t ncols,
+                                         uint32_t line0, uint32_t lane) {
+    __syncwarp();
+    uint32_t* dst = cv_blk + line0 + lane;
+    for (uint32_t col = 0u; col < ncols; col++) dst[(size_t)col * cv_pitch] = stg[lane * 33u + col];
+    __syncwarp();
+}
+// a tile's base vector: the window counts (<= 2r+1 <= 255) as bytes, by compact id
+template <int K>
+__device__ __noinline__ void vscan_dump(const uint32_t* st, uint8_t* dst8) {
+    uint4* dst = reinterpret_cast<uint4*>(dst8);
+#pragma unroll 2
+    for (int q = 0; q < 2 * K; q++) {
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t* src = st + (size_t)(16 * q + 4 * e) * kVscanThreads;
+            v[e] = (src[0] & 0xFFu) | ((src[kVscanThreads] & 0xFFu) << 8) | ((src[2 * kVscanThreads] & 0xFFu) << 16) |
+                   (src[3 * kVscanThreads] << 24);
+        }
+        dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 template <int K>
 struct VscanState {
     uint32_t* st;        // this thread's column of the state table
@@ -244,26 +270,20 @@ struct VscanState {
         for (int k = 0; k < K; k++) dst[k * 32 + lane] = tm[k * 32 + lane];
         __syncwarp();
     }
-    // a tile's base vector: the window counts (<= 2r+1 <= 255) as bytes, by compact id
-    __device__ __noinline__ void dump(uint8_t* dst8) const {
-        uint4* dst = reinterpret_cast<uint4*>(dst8);
-#pragma unroll 2
-        for (int q = 0; q < 2 * K; q++) {
-            uint32_t v[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const uint32_t* src = st + (size_t)(16 * q + 4 * e) * kVscanThreads;
-                v[e] = (src[0] & 0xFFu) | ((src[kVscanThreads] & 0xFFu) << 8) | ((src[2 * kVscanThreads] & 0xFFu) << 16) |
-                       (src[3 * kVscanThreads] << 24);
-            }
-            dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
-        }
-    }
+    // (compact id | chain start << 16) of every cell goes to a column-major map (a column's window is contiguous for
+    // events_kernel). 32 rows are staged in shared memory ([row][33] words) and leave as one 128-byte line per column.
+    uint32_t* stg;        // the warp's staging tile
+    uint32_t* cv_blk;     // the block's first column in the map, at index 0
+    uint32_t cv_pitch, ncols;
+    __device__ __forceinline__ void flush(uint32_t line0) const { vscan_flush(stg, cv_blk, cv_pitch, ncols, line0, lane); }
+    __device__ __forceinline__ void push(uint32_t idx, uint32_t value) const { stg[(idx & 31u) * 33u + lane] = value; }
+
+    __device__ __forceinline__ void dump(uint8_t* dst8) const { vscan_dump<K>(st, dst8); }
 };
 
 template <int K>
 __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint16_t* __restrict__ cmap,
-                                                              uint16_t* __restrict__ vstart, uint8_t* __restrict__ base,
+                                                              uint32_t* __restrict__ cvt, uint8_t* __restrict__ base,
                                                               uint32_t* __restrict__ tmask) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int Bpad = 32 * K;
@@ -275,6 +295,10 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     VscanState<K> vs;
     vs.st = reinterpret_cast<uint32_t*>(smem) + lane;
     vs.tm = reinterpret_cast<uint32_t*>(smem) + Bpad * T;
+    vs.stg = vs.tm + Bpad;
+    vs.cv_blk = cvt + ((size_t)n * g.PW + blockIdx.x * T) * g.cv_pitch;
+    vs.cv_pitch = g.cv_pitch;
+    vs.ncols = min((uint32_t)T, g.PW - blockIdx.x * T);
     vs.lanebit = valid ? 1u << lane : 0u;
     vs.lane = lane;
 #pragma unroll 8
@@ -284,7 +308,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     __syncwarp();
     const size_t P = g.P;
     const uint16_t* in = cmap + (size_t)n * g.PH * P + c;      // row p (entering)
-    uint16_t* vout = vstart + (size_t)n * g.PH * P + c;
+    uint32_t ci = g.cv_pad;   // index of row p in the column-major map: cv_pad + p (the 8-row groups start on a line)
     const uint32_t nblk = gridDim.x;
     uint32_t* mout = tmask + ((size_t)n * g.H * nblk + blockIdx.x) * Bpad;   // row y
     const size_t mstep = (size_t)nblk * Bpad;
@@ -300,17 +324,16 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         for (int j = 0; j < 8; j++) s_in[j] = in[j * P];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint32_t v0 = vs.enter(s_in[j], p + j);
-            if (valid) vout[j * P] = (uint16_t)v0;
+            vs.push(ci, s_in[j] | (vs.enter(s_in[j], p + j) << 16));
+            if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
         }
         in += 8 * P;
-        vout += 8 * P;
     }
     for (; p <= two_r; p++) {
-        const uint32_t v0 = vs.enter(*in, p);
-        if (valid) *vout = (uint16_t)v0;
+        const uint32_t sv = *in;
+        vs.push(ci, sv | (vs.enter(sv, p) << 16));
+        if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
         in += P;
-        vout += P;
     }
     vs.store_mask(mout);
     mout += mstep;
@@ -322,23 +345,39 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     uint32_t y = 1u;
     if (g.TY % 8u == 0u) {
         // groups of 8 rows ending on a multiple of 8, so that a tile's first row is always the last row of a group
+        // the samples of a group are loaded while the group before it is processed (one DRAM round trip hidden per group)
+        uint32_t n_in[8], n_out[8];
+        if (y + 8u <= g.H) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                n_in[j] = in[j * P];
+                n_out[j] = out[j * P];
+            }
+        }
         for (; y + 8u <= g.H; y += 8u) {
             uint32_t s_in[8], s_out[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                s_in[j] = in[j * P];
-                s_out[j] = out[j * P];
+                s_in[j] = n_in[j];
+                s_out[j] = n_out[j];
+            }
+            if (y + 16u <= g.H) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    n_in[j] = in[(8 + j) * P];
+                    n_out[j] = out[(8 + j) * P];
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t v0 = vs.enter(s_in[j], two_r + y + j);
-                if (valid) vout[j * P] = (uint16_t)v0;
+                vs.push(ci + j, s_in[j] | (vs.enter(s_in[j], two_r + y + j) << 16));
                 vs.leave(s_out[j]);
                 vs.store_mask(mout + j * mstep);
             }
+            ci += 8u;
+            if ((ci & 31u) == 0u) vs.flush(ci - 32u);
             in += 8 * P;
             out += 8 * P;
-            vout += 8 * P;
             mout += 8 * mstep;
             if ((y + 7u) % g.TY == 0u) {
                 if (valid) vs.dump(bout);
@@ -347,19 +386,20 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         }
     }
     for (; y < g.H; y++) {
-        const uint32_t v0 = vs.enter(*in, two_r + y);
-        if (valid) *vout = (uint16_t)v0;
+        const uint32_t sv = *in;
+        vs.push(ci, sv | (vs.enter(sv, two_r + y) << 16));
+        if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
         vs.leave(*out);
         vs.store_mask(mout);
         in += P;
         out += P;
-        vout += P;
         mout += mstep;
         if (y % g.TY == 0u) {
             if (valid) vs.dump(bout);
             bout += bstep;
         }
     }
+    if (ci & 31u) vs.flush(ci & ~31u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -110,6 +110,18 @@ namespace SuperTerrainPlus::STPAlgorithm {
 		STPSingleHistogram filterBatch(const STPSample_t* const*, unsigned int chunk_count, const STPNearestNeighbourInformation&,
 			STPFilterBuffer&, unsigned int);
 
+		//the filter fed by the UNMERGED neighbour chunk maps: `neighbour_map` holds chunk_count * nn.x * nn.y pointers
+		//(host or device memory), neighbour i of a neighbourhood at local coordinate (i % nn.x, i / nn.x) exactly as
+		//STPNearestNeighbourTextureBuffer takes them, every map MapSize.x * MapSize.y samples. Replaces the merged
+		//page-locked copy of STPNearestNeighbourTextureBuffer::STPMergedBuffer in front of operator(): only the centre
+		//chunk and its halo of `radius` samples are moved. nn_info.TotalMapSize is not used.
+		STPSingleHistogram filterNeighbours(const STPSample_t* const* neighbour_map, unsigned int chunk_count,
+			const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int radius);
+
+		//same, result left in device memory (readDeviceHistogram); copies and kernels are enqueued on `stream`
+		void filterNeighboursDevice(const STPSample_t* const* neighbour_map, unsigned int chunk_count,
+			const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int radius, void* stream = nullptr);
+
 		//merged maps already in device memory (chunk i at samplemap_device + i * chunk_stride samples); the result stays
 		//in device memory (readDeviceHistogram). `stream` is a cudaStream_t; the call returns once the work is enqueued.
 		void filterDevice(const STPSample_t* samplemap_device, std::uint64_t chunk_stride, unsigned int chunk_count,

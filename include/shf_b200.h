@@ -97,6 +97,22 @@ SHF_API int shf_run_device(shf_filter* filter, const uint16_t* samplemaps_dev, u
                            const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
                            const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius, void* stream);
 
+/* Neighbour merge without the merged host buffer (replaces the pack step of
+ * STPNearestNeighbourTextureBuffer::STPMergedBuffer, SuperTerrain+/Private/World/Chunk/
+ * STPNearestNeighbourTextureBuffer.cpp:18-39,70-113, in front of the filter call at SuperDemo+/World/Biomes/
+ * STPBiomefieldGenerator.cpp:94-104). neighbour_maps holds n_chunks * nn.x * nn.y pointers: neighbour i of a
+ * neighbourhood sits at local coordinate (i % nn.x, i / nn.x) (STPChunk::calcLocalChunkCoordinate, STPChunk.cpp:71-73),
+ * every map is MapSize.x * MapSize.y samples, row-major, in HOST or DEVICE memory. Only the centre chunk and a halo of
+ * `radius` samples are copied, directly into the device input. Same result and errors as shf_run_batch on the merged
+ * maps; result in page-locked host memory. */
+SHF_API int shf_run_neighbours(shf_filter* filter, const uint16_t* const* neighbour_maps, uint32_t n_chunks,
+                               const uint32_t map_size[2], const uint32_t nearest_neighbour[2], shf_buffer* buffer,
+                               uint32_t radius);
+/* Same, result left in device memory (shf_buffer_read_device); copies and kernels are enqueued on `stream`. */
+SHF_API int shf_run_neighbours_device(shf_filter* filter, const uint16_t* const* neighbour_maps, uint32_t n_chunks,
+                                      const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
+                                      shf_buffer* buffer, uint32_t radius, void* stream);
+
 /* Device pointers of the last result (bins concatenated, offsets n_chunks x (W*H+1)). */
 SHF_API int shf_buffer_read_device(const shf_buffer* buffer, const shf_bin** bins_dev, const uint32_t** offsets_dev);
 /* Host array of n_chunks+1 first-bin indices (last = total bins) of the last result. */

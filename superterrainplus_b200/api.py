@@ -32,7 +32,8 @@ SHF_ERR_OFFSET_OVERFLOW, SHF_ERR_UNSUPPORTED, SHF_ERR_INVALID_ARGUMENT = 4, 5, 6
 # every symbol include/shf_b200.h declares (tests check the library exports exactly these)
 C_ABI_SYMBOLS = (
     "shf_filter_create", "shf_filter_destroy", "shf_buffer_create", "shf_buffer_destroy", "shf_buffer_read",
-    "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_buffer_read_device",
+    "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_run_neighbours",
+    "shf_run_neighbours_device", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
     "shf_set_profiling", "shf_buffer_phase_ms", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
 )
@@ -92,6 +93,8 @@ def library() -> ctypes.CDLL:
     lib.shf_run.argtypes = [vp, vp, _U32x2, _U32x2, _U32x2, vp, u32]
     lib.shf_run_batch.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, _U32x2, vp, u32]
     lib.shf_run_device.argtypes = [vp, vp, u64, u32, _U32x2, _U32x2, _U32x2, vp, u32, vp]
+    lib.shf_run_neighbours.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32]
+    lib.shf_run_neighbours_device.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32, vp]
     lib.shf_buffer_read_device.argtypes = [vp, P(vp), P(vp)]
     lib.shf_buffer_chunk_base.argtypes = [vp, P(vp), P(u32)]
     lib.shf_last_error.restype = ctypes.c_char_p
@@ -277,6 +280,33 @@ class STPSingleHistogramFilter:
                                        _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
                                        filter_buffer._h, radius))
         return filter_buffer.readHistogram()
+
+    def runNeighbours(self, neighbour_maps: Sequence, nn_info: STPNearestNeighbourInformation,
+                      filter_buffer: "STPFilterBuffer", radius: int) -> STPSingleHistogram:
+        """The filter fed by the UNMERGED chunk maps (additive; shf_run_neighbours).
+        neighbour_maps: for every neighbourhood its nn.x * nn.y chunk maps (MapSize.y x MapSize.x uint16 each) in
+        local-index order (i % nn.x, i / nn.x), i.e. what STPNearestNeighbourTextureBuffer is constructed from; a flat
+        sequence of n * nn.x * nn.y arrays. Only the centre chunk + halo travel to the device, no merged host buffer."""
+        w, h = nn_info.MapSize
+        per = nn_info.ChunkNearestNeighbour[0] * nn_info.ChunkNearestNeighbour[1]
+        maps = [np.ascontiguousarray(m, dtype=np.uint16) for m in neighbour_maps]
+        if not maps or len(maps) % per or any(m.size != w * h for m in maps):
+            raise ValueError("neighbour_maps must hold n * nn.x * nn.y maps of MapSize samples each")
+        arr = (ctypes.c_void_p * len(maps))(*[m.ctypes.data for m in maps])
+        _check(library().shf_run_neighbours(self._h, arr, len(maps) // per, _U32x2(*nn_info.MapSize),
+                                            _U32x2(*nn_info.ChunkNearestNeighbour), filter_buffer._h, radius))
+        return filter_buffer.readHistogram()
+
+    def runNeighboursDevice(self, neighbour_ptrs: Sequence[int], nn_info: STPNearestNeighbourInformation,
+                            filter_buffer: "STPFilterBuffer", radius: int, stream: int = 0) -> None:
+        """Same from raw pointers (host or device memory), result left in device memory (shf_run_neighbours_device)."""
+        per = nn_info.ChunkNearestNeighbour[0] * nn_info.ChunkNearestNeighbour[1]
+        if not neighbour_ptrs or len(neighbour_ptrs) % per:
+            raise ValueError("neighbour_ptrs must hold n * nn.x * nn.y pointers")
+        arr = (ctypes.c_void_p * len(neighbour_ptrs))(*neighbour_ptrs)
+        _check(library().shf_run_neighbours_device(self._h, arr, len(neighbour_ptrs) // per, _U32x2(*nn_info.MapSize),
+                                                   _U32x2(*nn_info.ChunkNearestNeighbour), filter_buffer._h, radius,
+                                                   stream))
 
     def runDevice(self, device_ptr: int, chunk_stride: int, n_chunks: int, nn_info: STPNearestNeighbourInformation,
                   filter_buffer: "STPFilterBuffer", radius: int, stream: int = 0) -> None:

@@ -475,6 +475,21 @@ int bind_device(const shf_filter* f, shf_buffer* b) {
     return SHF_OK;
 }
 
+// the result of the last run_on_device into the buffer's page-locked host memory (what readHistogram() hands out)
+int result_to_host(shf_buffer* b, cudaStream_t s) {
+    SHF_CUDA(b->h_bins.ensure(std::max<size_t>(b->n_bins, 1) * sizeof(shf_bin)));
+    SHF_CUDA(b->h_hso.ensure(b->n_offsets * 4));
+    if (b->n_bins) {
+        SHF_CUDA(cudaMemcpyAsync(b->h_bins.p, b->bins.p, b->n_bins * sizeof(shf_bin), cudaMemcpyDeviceToHost, s));
+        tls_d2h += b->n_bins * sizeof(shf_bin);
+    }
+    SHF_CUDA(cudaMemcpyAsync(b->h_hso.p, b->hso.p, b->n_offsets * 4, cudaMemcpyDeviceToHost, s));
+    tls_d2h += b->n_offsets * 4;
+    SHF_CUDA(cudaStreamSynchronize(s));
+    b->on_host = true;
+    return SHF_OK;
+}
+
 int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, const uint32_t map_size[2],
              const uint32_t nn[2], const uint32_t total[2], shf_buffer* b, uint32_t radius) {
     if (!f || !b || !maps || !map_size || !nn || !total)
@@ -501,18 +516,58 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
     }
     st = run_on_device(f, b, b->din.as<uint16_t>(), cells, P, n_chunks, W, H, r, s);
     if (st != SHF_OK) return st;
-    // result to page-locked host memory
-    SHF_CUDA(b->h_bins.ensure(std::max<size_t>(b->n_bins, 1) * sizeof(shf_bin)));
-    SHF_CUDA(b->h_hso.ensure(b->n_offsets * 4));
-    if (b->n_bins) {
-        SHF_CUDA(cudaMemcpyAsync(b->h_bins.p, b->bins.p, b->n_bins * sizeof(shf_bin), cudaMemcpyDeviceToHost, s));
-        tls_d2h += b->n_bins * sizeof(shf_bin);
+    return result_to_host(b, s);
+}
+
+// Neighbour merge on the device side of the bus. The reference packs the nn.x * nn.y chunk
+// maps into one page-locked host buffer first (STPNearestNeighbourTextureBuffer.cpp:70-113: cudaMallocHost + 9 host to
+// host 2D copies + sync) and the filter then walks that buffer. Here only the cells the filter reads -- the centre chunk
+// plus a halo of `radius` cells -- are copied, straight from every neighbour's own map into the halo-extended device
+// input: no merged host buffer, no page-locked allocation, (W+2r)(H+2r) instead of nn.x*nn.y*W*H cells moved.
+// chunk_maps: n_chunks * nn.x * nn.y pointers (host or device memory, cudaMemcpyDefault), neighbour i of a neighbourhood
+// at local coordinate (i % nn.x, i / nn.x) as in STPChunk::calcLocalChunkCoordinate, each map W x H row-major.
+int gather_neighbours(shf_filter* f, shf_buffer* b, const uint16_t* const* chunk_maps, uint32_t n_chunks,
+                      const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius, cudaStream_t s) {
+    const uint32_t W = map_size[0], H = map_size[1], r = radius;
+    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 7u) & ~7u;
+    const size_t x0 = (size_t)W * (nn[0] / 2u) - r, y0 = (size_t)H * (nn[1] / 2u) - r;  // halo origin in the merged map
+    const size_t cells = (size_t)PH * P;
+    const uint32_t per = nn[0] * nn[1];
+    SHF_CUDA(b->din.ensure((size_t)n_chunks * cells * 2));
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        uint16_t* dst0 = b->din.as<uint16_t>() + (size_t)i * cells;
+        for (uint32_t k = 0; k < per; k++) {
+            const size_t cx = (size_t)(k % nn[0]) * W, cy = (size_t)(k / nn[0]) * H;  // the neighbour's origin
+            const size_t xa = std::max(cx, x0), xb = std::min(cx + W, x0 + PW);
+            const size_t ya = std::max(cy, y0), yb = std::min(cy + H, y0 + PH);
+            if (xa >= xb || ya >= yb) continue;  // this neighbour lies outside the halo
+            const uint16_t* map = chunk_maps[(size_t)i * per + k];
+            if (!map) return fail(SHF_ERR_INVALID_ARGUMENT, "neighbour map != NULL", "null neighbour sample map");
+            SHF_CUDA(cudaMemcpy2DAsync(dst0 + (ya - y0) * P + (xa - x0), (size_t)P * 2, map + (ya - cy) * W + (xa - cx),
+                                       (size_t)W * 2, (xb - xa) * 2, yb - ya, cudaMemcpyDefault, s));
+            tls_h2d += (xb - xa) * 2 * (yb - ya);
+        }
     }
-    SHF_CUDA(cudaMemcpyAsync(b->h_hso.p, b->hso.p, b->n_offsets * 4, cudaMemcpyDeviceToHost, s));
-    tls_d2h += b->n_offsets * 4;
-    SHF_CUDA(cudaStreamSynchronize(s));
-    b->on_host = true;
+    (void)f;
     return SHF_OK;
+}
+
+int run_neighbours(shf_filter* f, const uint16_t* const* chunk_maps, uint32_t n_chunks, const uint32_t map_size[2],
+                   const uint32_t nn[2], shf_buffer* b, uint32_t radius, cudaStream_t user_stream, bool to_host) {
+    if (!f || !b || !chunk_maps || !map_size || !nn) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "n_chunks > 0", "empty batch");
+    int st = validate(map_size, nn, radius);
+    if (st != SHF_OK) return st;
+    st = bind_device(f, b);
+    if (st != SHF_OK) return st;
+    b->has_result = false;
+    cudaStream_t s = to_host ? b->stream : user_stream;
+    st = gather_neighbours(f, b, chunk_maps, n_chunks, map_size, nn, radius, s);
+    if (st != SHF_OK) return st;
+    const uint32_t PW = map_size[0] + 2u * radius, PH = map_size[1] + 2u * radius, P = (PW + 7u) & ~7u;
+    st = run_on_device(f, b, b->din.as<uint16_t>(), (size_t)PH * P, P, n_chunks, map_size[0], map_size[1], radius, s);
+    if (st != SHF_OK) return st;
+    return to_host ? result_to_host(b, s) : SHF_OK;
 }
 
 }  // namespace
@@ -620,6 +675,17 @@ int shf_run_device(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_strid
     b->has_result = false;
     const uint16_t* view = maps_dev + (sy - radius) * S + (sx - radius);
     return run_on_device(f, b, view, chunk_stride, (uint32_t)S, n_chunks, W, H, radius, static_cast<cudaStream_t>(stream));
+}
+
+int shf_run_neighbours(shf_filter* filter, const uint16_t* const* neighbour_maps, uint32_t n_chunks,
+                       const uint32_t map_size[2], const uint32_t nn[2], shf_buffer* buffer, uint32_t radius) {
+    return run_neighbours(filter, neighbour_maps, n_chunks, map_size, nn, buffer, radius, nullptr, true);
+}
+
+int shf_run_neighbours_device(shf_filter* filter, const uint16_t* const* neighbour_maps, uint32_t n_chunks,
+                              const uint32_t map_size[2], const uint32_t nn[2], shf_buffer* buffer, uint32_t radius,
+                              void* stream) {
+    return run_neighbours(filter, neighbour_maps, n_chunks, map_size, nn, buffer, radius, static_cast<cudaStream_t>(stream), false);
 }
 
 int shf_buffer_read_device(const shf_buffer* b, const shf_bin** bins_dev, const uint32_t** offsets_dev) {

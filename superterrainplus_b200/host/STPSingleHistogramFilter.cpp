@@ -124,6 +124,21 @@ STPSingleHistogram STPSingleHistogramFilter::filterBatch(const STPSample_t* cons
 	return filter_buffer.readHistogram();
 }
 
+STPSingleHistogram STPSingleHistogramFilter::filterNeighbours(const STPSample_t* const* const neighbour_map,
+	const unsigned int chunk_count, const STPNearestNeighbourInformation& nn_info, STPFilterBuffer& filter_buffer,
+	const unsigned int radius) {
+	const STPGeometry geo(nn_info);
+	check(shf_run_neighbours(this->Filter, neighbour_map, chunk_count, geo.MapSize, geo.Neighbour, filter_buffer.Memory, radius));
+	return filter_buffer.readHistogram();
+}
+
+void STPSingleHistogramFilter::filterNeighboursDevice(const STPSample_t* const* const neighbour_map, const unsigned int chunk_count,
+	const STPNearestNeighbourInformation& nn_info, STPFilterBuffer& filter_buffer, const unsigned int radius, void* const stream) {
+	const STPGeometry geo(nn_info);
+	check(shf_run_neighbours_device(this->Filter, neighbour_map, chunk_count, geo.MapSize, geo.Neighbour, filter_buffer.Memory,
+		radius, stream));
+}
+
 void STPSingleHistogramFilter::filterDevice(const STPSample_t* const samplemap_device, const std::uint64_t chunk_stride,
 	const unsigned int chunk_count, const STPNearestNeighbourInformation& nn_info, STPFilterBuffer& filter_buffer,
 	const unsigned int radius, void* const stream) {

@@ -103,6 +103,25 @@ static void compareWithOracle(STPSingleHistogramFilter& filter, const unsigned i
 		same = bins[i].item == result.Bin[i].Item && std::memcmp(&bins[i].weight, &result.Bin[i].Weight, sizeof(float)) == 0;
 	}
 	REQUIRE(same);
+	//the same neighbourhood handed over as its nine separate chunk maps (what STPNearestNeighbourTextureBuffer is built
+	//from, STPNearestNeighbourTextureBuffer.cpp:70-113) must give the very same histogram
+	std::vector<std::vector<STPSample_t>> chunk(9u, std::vector<STPSample_t>(size_t(w) * h));
+	const STPSample_t* chunk_ptr[9];
+	for (unsigned int i = 0u; i < 9u; i++) {
+		const unsigned int cx = i % 3u, cy = i / 3u;
+		for (unsigned int y = 0u; y < h; y++) {
+			std::memcpy(chunk[i].data() + size_t(y) * w, map.data() + (size_t(cy) * h + y) * 3u * w + size_t(cx) * w, w * sizeof(STPSample_t));
+		}
+		chunk_ptr[i] = chunk[i].data();
+	}
+	FiltBuf unmerged(Exec::Serial);
+	const STPSingleHistogram again = filter.filterNeighbours(chunk_ptr, 1u, info, unmerged, radius);
+	bool same_unmerged = unmerged.size().first == n_bins
+		&& std::memcmp(offsets, again.HistogramStartOffset, offset_count * sizeof(uint32_t)) == 0;
+	for (uint64_t i = 0u; same_unmerged && i < n_bins; i++) {
+		same_unmerged = bins[i].item == again.Bin[i].Item && std::memcmp(&bins[i].weight, &again.Bin[i].Weight, sizeof(float)) == 0;
+	}
+	REQUIRE(same_unmerged);
 	shf_oracle_free(bins);
 	shf_oracle_free(offsets);
 }

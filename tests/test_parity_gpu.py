@@ -181,6 +181,72 @@ def test_batch_matches_single(shf, filt, oracle_mod):
     buf.close()
 
 
+def split_neighbours(m, w, h, nn):
+    """The nn.x * nn.y chunk maps of a merged map, in local-index order (STPChunk::calcLocalChunkCoordinate)."""
+    return [np.ascontiguousarray(m[cy * h:(cy + 1) * h, cx * w:(cx + 1) * w]) for cy in range(nn[1]) for cx in range(nn[0])]
+
+
+@pytest.mark.parametrize("w,h,r,nn,biomes,kind", [
+    (16, 12, 4, (3, 3), 9, "iid"), (33, 20, 20, (3, 3), 6, "blocky"), (24, 24, 24, (3, 3), 40, "iid"),
+    (10, 14, 10, (5, 3), 7, "rare"), (8, 8, 16, (5, 5), 5, "blocky"), (40, 36, 8, (3, 5), 300, "iid"),
+])
+def test_unmerged_neighbours_match_merged(shf, filt, oracle_mod, w, h, r, nn, biomes, kind):
+    """Row f2: the filter fed by the separate chunk maps (no merged buffer) == the filter on the merged map == oracle.
+    Covers halos that span more than one neighbour (r > W with 5 neighbours across) and the wide path (300 values)."""
+    rng = np.random.default_rng(w * 1000 + h * 10 + r)
+    info = nn_info(shf, w, h, nn)
+    maps = [random_map(rng, w, h, biomes, kind, nn) for _ in range(3)]
+    want = [oracle_mod.run_port(m, (w, h), nn, r) for m in maps]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(shf.STPSingleHistogramFilter.STPFilterBuffer.STPExecutionType.Parallel)
+    flat = [c for m in maps for c in split_neighbours(m, w, h, nn)]
+    hist = filt.runNeighbours(flat, info, buf, r)
+    base = buf.chunkBase()
+    stride = w * h + 1
+    for i, wnt in enumerate(want):
+        lo, hi = int(base[i]), int(base[i + 1])
+        got = (hist.Bin["Item"][lo:hi].copy(), hist.Bin["Weight"][lo:hi].copy(),
+               hist.HistogramStartOffset[i * stride:(i + 1) * stride].copy())
+        assert_same(got, wnt, f"unmerged neighbourhood {i}")
+    # a single neighbourhood through the same entry point, and the argument checks
+    one = filt.runNeighbours(split_neighbours(maps[1], w, h, nn), info, buf, r)
+    assert_same(split_result(one), want[1], "single unmerged neighbourhood")
+    with pytest.raises(shf.STPNumericDomainError):
+        filt.runNeighbours(split_neighbours(maps[0], w, h, nn), info, buf, 3)
+    with pytest.raises(ValueError):
+        filt.runNeighbours(flat[:-1], info, buf, r)
+
+
+def test_unmerged_neighbours_from_device_memory(shf, filt, oracle_mod):
+    """The same entry point with the chunk maps already in device memory and the result left there."""
+    import torch
+
+    w, h, r, nn, biomes = 64, 48, 32, (3, 3), 20
+    rng = np.random.default_rng(99)
+    info = nn_info(shf, w, h, nn)
+    maps = [random_map(rng, w, h, biomes, "blocky", nn) for _ in range(2)]
+    chunks = [torch.from_numpy(c.view(np.int16)).cuda() for m in maps for c in split_neighbours(m, w, h, nn)]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(shf.STPSingleHistogramFilter.STPFilterBuffer.STPExecutionType.Parallel)
+    stream = torch.cuda.current_stream().cuda_stream
+    filt.runNeighboursDevice([c.data_ptr() for c in chunks], info, buf, r, stream)
+    torch.cuda.synchronize()
+    bins_p, offs_p = buf.readDevice()
+    n_bins, n_offs = buf.size()
+    bins = torch.empty(n_bins * 8, dtype=torch.uint8, device="cuda")
+    offs = torch.empty(n_offs, dtype=torch.int32, device="cuda")
+    import ctypes
+    cudart = ctypes.CDLL("libcudart.so.12")
+    assert cudart.cudaMemcpy(ctypes.c_void_p(bins.data_ptr()), ctypes.c_void_p(bins_p), ctypes.c_size_t(n_bins * 8), 3) == 0
+    assert cudart.cudaMemcpy(ctypes.c_void_p(offs.data_ptr()), ctypes.c_void_p(offs_p), ctypes.c_size_t(n_offs * 4), 3) == 0
+    rec = bins.cpu().numpy().view(shf.BIN_DTYPE)
+    items, weights, offsets = rec["Item"].copy(), rec["Weight"].copy(), offs.cpu().numpy().view(np.uint32)
+    base = buf.chunkBase()
+    stride = w * h + 1
+    for i, m in enumerate(maps):
+        lo, hi = int(base[i]), int(base[i + 1])
+        assert_same((items[lo:hi], weights[lo:hi], offsets[i * stride:(i + 1) * stride]),
+                    oracle_mod.run_port(m, (w, h), nn, r), f"device neighbourhood {i}")
+
+
 def test_device_resident(shf, filt, oracle_mod):
     import torch
 

@@ -110,6 +110,13 @@ namespace SuperTerrainPlus::STPAlgorithm {
 		STPSingleHistogram filterBatch(const STPSample_t* const*, unsigned int chunk_count, const STPNearestNeighbourInformation&,
 			STPFilterBuffer&, unsigned int);
 
+		//`call_count` concurrent operator() calls served by one pass over the device: samplemap[i] / filter_buffer[i] are
+		//what call i would hand to operator(); all share nn_info and radius, the buffers are distinct. Afterwards every
+		//filter_buffer[i] reads exactly as after operator()(samplemap[i], nn_info, *filter_buffer[i], radius).
+		//(STPSingleHistogramBatcher turns concurrent operator() calls into this.)
+		void filterMulti(const STPSample_t* const* samplemap, STPFilterBuffer* const* filter_buffer, unsigned int call_count,
+			const STPNearestNeighbourInformation&, unsigned int radius);
+
 		//the filter fed by the UNMERGED neighbour chunk maps: `neighbour_map` holds chunk_count * nn.x * nn.y pointers
 		//(host or device memory), neighbour i of a neighbourhood at local coordinate (i % nn.x, i / nn.x) exactly as
 		//STPNearestNeighbourTextureBuffer takes them, every map MapSize.x * MapSize.y samples. Replaces the merged

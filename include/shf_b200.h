@@ -97,6 +97,18 @@ SHF_API int shf_run_device(shf_filter* filter, const uint16_t* samplemaps_dev, u
                            const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
                            const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius, void* stream);
 
+/* n_calls concurrent operator() calls served by ONE pass over the device (the world
+ * pipeline runs up to five STPBiomefieldGenerator::operator() at once, SuperDemo+/World/Biomes/
+ * STPBiomefieldGenerator.cpp:79-104, SuperTerrain+/Private/World/STPWorldPipeline.cpp:448-474, every one with its own
+ * pooled STPFilterBuffer). samplemaps[i] / buffers[i] are the arguments call i would pass to shf_run; all calls share the
+ * geometry and the radius. On SHF_OK every buffers[i] reads exactly as after shf_run(filter, samplemaps[i], ...,
+ * buffers[i], radius): its own chunk's bins and offsets in its own page-locked memory, size() = (its bins, W*H+1).
+ * Device scratch is taken from buffers[0]; only buffers[0] keeps a device-resident view (of its own chunk). The buffers
+ * must be distinct. */
+SHF_API int shf_run_multi(shf_filter* filter, const uint16_t* const* samplemaps, shf_buffer* const* buffers,
+                          uint32_t n_calls, const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
+                          const uint32_t total_map_size[2], uint32_t radius);
+
 /* Neighbour merge without the merged host buffer (replaces the pack step of
  * STPNearestNeighbourTextureBuffer::STPMergedBuffer, SuperTerrain+/Private/World/Chunk/
  * STPNearestNeighbourTextureBuffer.cpp:18-39,70-113, in front of the filter call at SuperDemo+/World/Biomes/

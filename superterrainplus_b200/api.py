@@ -33,7 +33,7 @@ SHF_ERR_OFFSET_OVERFLOW, SHF_ERR_UNSUPPORTED, SHF_ERR_INVALID_ARGUMENT = 4, 5, 6
 C_ABI_SYMBOLS = (
     "shf_filter_create", "shf_filter_destroy", "shf_buffer_create", "shf_buffer_destroy", "shf_buffer_read",
     "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_run_neighbours",
-    "shf_run_neighbours_device", "shf_buffer_read_device",
+    "shf_run_neighbours_device", "shf_run_multi", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
     "shf_set_profiling", "shf_buffer_phase_ms", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
 )
@@ -94,6 +94,7 @@ def library() -> ctypes.CDLL:
     lib.shf_run_batch.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, _U32x2, vp, u32]
     lib.shf_run_device.argtypes = [vp, vp, u64, u32, _U32x2, _U32x2, _U32x2, vp, u32, vp]
     lib.shf_run_neighbours.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32]
+    lib.shf_run_multi.argtypes = [vp, P(vp), P(vp), u32, _U32x2, _U32x2, _U32x2, u32]
     lib.shf_run_neighbours_device.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32, vp]
     lib.shf_buffer_read_device.argtypes = [vp, P(vp), P(vp)]
     lib.shf_buffer_chunk_base.argtypes = [vp, P(vp), P(u32)]
@@ -280,6 +281,20 @@ class STPSingleHistogramFilter:
                                        _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
                                        filter_buffer._h, radius))
         return filter_buffer.readHistogram()
+
+    def runMulti(self, samplemaps: Sequence, nn_info: STPNearestNeighbourInformation, filter_buffers: Sequence,
+                 radius: int) -> list:
+        """len(samplemaps) concurrent operator() calls served by one device pass (additive; shf_run_multi, SURVEY.md
+        section 8 row f3): afterwards filter_buffers[i] reads as if self(samplemaps[i], nn_info, filter_buffers[i], radius)
+        had been called. Returns the per-call histograms."""
+        maps = [self._host_map(m, nn_info) for m in samplemaps]
+        if len(maps) != len(filter_buffers):
+            raise ValueError("one filter buffer per sample map")
+        arr = (ctypes.c_void_p * len(maps))(*[m.ctypes.data for m in maps])
+        bufs = (ctypes.c_void_p * len(maps))(*[b._h.value for b in filter_buffers])
+        _check(library().shf_run_multi(self._h, arr, bufs, len(maps), _U32x2(*nn_info.MapSize),
+                                       _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize), radius))
+        return [b.readHistogram() for b in filter_buffers]
 
     def runNeighbours(self, neighbour_maps: Sequence, nn_info: STPNearestNeighbourInformation,
                       filter_buffer: "STPFilterBuffer", radius: int) -> STPSingleHistogram:

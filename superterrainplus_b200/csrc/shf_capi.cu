@@ -113,6 +113,7 @@ struct shf_buffer {
     size_t n_bins = 0, n_offsets = 0;
     DevBuf hf_offsets;  // per-chunk noise offsets of shf_heightfield_run
     bool has_result = false, on_host = false;
+    bool dev_valid = false;  // the device arrays hold this buffer's result (not so for the followers of shf_run_multi)
     uint32_t plan_k = 0, plan_ty = 0, plan_biomes = 0, plan_smem = 0;
     cudaEvent_t ev[kPhases + 1] = {};
     bool ev_valid = false;
@@ -296,6 +297,7 @@ int publish(shf_buffer* b, const Geo& g) {
     b->n_bins = (size_t)b->chunk_base[g.n_chunks];
     b->n_offsets = (size_t)g.n_chunks * ((size_t)g.W * g.H + 1u);
     b->has_result = true;
+    b->dev_valid = true;
     b->on_host = false;
     return SHF_OK;
 }
@@ -491,7 +493,7 @@ int result_to_host(shf_buffer* b, cudaStream_t s) {
 }
 
 int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, const uint32_t map_size[2],
-             const uint32_t nn[2], const uint32_t total[2], shf_buffer* b, uint32_t radius) {
+             const uint32_t nn[2], const uint32_t total[2], shf_buffer* b, uint32_t radius, bool to_host = true) {
     if (!f || !b || !maps || !map_size || !nn || !total)
         return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
     int st = validate(map_size, nn, radius);
@@ -516,7 +518,61 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
     }
     st = run_on_device(f, b, b->din.as<uint16_t>(), cells, P, n_chunks, W, H, r, s);
     if (st != SHF_OK) return st;
-    return result_to_host(b, s);
+    return to_host ? result_to_host(b, s) : SHF_OK;
+}
+
+// Several concurrent operator() calls of the world pipeline served by one pass: the
+// neighbourhoods go through the kernels as one batch on buffers[0], then every caller's buffer receives its own chunk's
+// bins and offsets in its own page-locked memory, exactly as if shf_run had been called on it.
+int run_multi(shf_filter* f, const uint16_t* const* maps, shf_buffer* const* buffers, uint32_t n_calls,
+              const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], uint32_t radius) {
+    if (!f || !maps || !buffers || !map_size || !nn || !total)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (n_calls == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "n_calls > 0", "empty batch");
+    for (uint32_t i = 0; i < n_calls; i++) {
+        if (!buffers[i]) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer != NULL", "null filter buffer");
+        for (uint32_t j = 0; j < i; j++)
+            if (buffers[i] == buffers[j])
+                return fail(SHF_ERR_INVALID_ARGUMENT, "buffers are distinct", "one filter buffer serves one call at a time");
+    }
+    shf_buffer* lead = buffers[0];
+    int st = run_host(f, maps, n_calls, map_size, nn, total, lead, radius, false);
+    if (st != SHF_OK) return st;
+    cudaStream_t s = lead->stream;
+    const size_t per = (size_t)map_size[0] * map_size[1] + 1u;
+    const std::vector<uint64_t> base = lead->chunk_base;
+    for (uint32_t i = 0; i < n_calls; i++) {
+        shf_buffer* b = buffers[i];
+        if (i) {
+            st = bind_device(f, b);
+            if (st != SHF_OK) return st;
+            b->has_result = false;
+        }
+        const size_t nb = (size_t)(base[i + 1u] - base[i]);
+        SHF_CUDA(b->h_bins.ensure(std::max<size_t>(nb, 1) * sizeof(shf_bin)));
+        SHF_CUDA(b->h_hso.ensure(per * 4));
+        if (nb) {
+            SHF_CUDA(cudaMemcpyAsync(b->h_bins.p, lead->bins.as<shf_bin>() + base[i], nb * sizeof(shf_bin), cudaMemcpyDeviceToHost, s));
+            tls_d2h += nb * sizeof(shf_bin);
+        }
+        SHF_CUDA(cudaMemcpyAsync(b->h_hso.p, lead->hso.as<uint32_t>() + (size_t)i * per, per * 4, cudaMemcpyDeviceToHost, s));
+        tls_d2h += per * 4;
+    }
+    SHF_CUDA(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n_calls; i++) {
+        shf_buffer* b = buffers[i];
+        b->n_chunks = 1u;
+        b->last_w = map_size[0];
+        b->last_h = map_size[1];
+        b->n_bins = (size_t)(base[i + 1u] - base[i]);
+        b->n_offsets = per;
+        b->chunk_base.assign({0ull, (uint64_t)b->n_bins});
+        b->has_result = true;
+        b->on_host = true;
+        b->dev_valid = i == 0u;  // chunk 0 sits at the start of the leader's device arrays
+        b->ev_valid = b->ev_valid && i == 0u;
+    }
+    return SHF_OK;
 }
 
 // Neighbour merge on the device side of the bus. The reference packs the nn.x * nn.y chunk
@@ -677,6 +733,11 @@ int shf_run_device(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_strid
     return run_on_device(f, b, view, chunk_stride, (uint32_t)S, n_chunks, W, H, radius, static_cast<cudaStream_t>(stream));
 }
 
+int shf_run_multi(shf_filter* filter, const uint16_t* const* samplemaps, shf_buffer* const* buffers, uint32_t n_calls,
+                  const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], uint32_t radius) {
+    return run_multi(filter, samplemaps, buffers, n_calls, map_size, nn, total, radius);
+}
+
 int shf_run_neighbours(shf_filter* filter, const uint16_t* const* neighbour_maps, uint32_t n_chunks,
                        const uint32_t map_size[2], const uint32_t nn[2], shf_buffer* buffer, uint32_t radius) {
     return run_neighbours(filter, neighbour_maps, n_chunks, map_size, nn, buffer, radius, nullptr, true);
@@ -690,8 +751,8 @@ int shf_run_neighbours_device(shf_filter* filter, const uint16_t* const* neighbo
 
 int shf_buffer_read_device(const shf_buffer* b, const shf_bin** bins_dev, const uint32_t** offsets_dev) {
     if (!b || !bins_dev || !offsets_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
-    *bins_dev = b->has_result ? b->bins.as<shf_bin>() : nullptr;
-    *offsets_dev = b->has_result ? b->hso.as<uint32_t>() : nullptr;
+    *bins_dev = b->has_result && b->dev_valid ? b->bins.as<shf_bin>() : nullptr;
+    *offsets_dev = b->has_result && b->dev_valid ? b->hso.as<uint32_t>() : nullptr;
     return SHF_OK;
 }
 
@@ -749,7 +810,8 @@ void shf_heightfield_destroy(shf_heightfield* h) {
 int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk, uint32_t n_chunks, const float* offsets_xy,
                         float* height_dev, void* stream) {
     if (!h || !b || !offsets_xy || !height_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
-    if (!b->has_result) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer holds a result", "run the filter on this buffer first");
+    if (!b->has_result || !b->dev_valid)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "buffer holds a device result", "run the filter on this buffer first");
     if (b->device != h->device) return fail(SHF_ERR_INVALID_ARGUMENT, "same device", "histogram and generator live on different devices");
     if (n_chunks == 0u || first_chunk > b->n_chunks || n_chunks > b->n_chunks - first_chunk || n_chunks > 65535u)
         return fail(SHF_ERR_INVALID_ARGUMENT, "chunk range inside the last result", "no such chunks");

@@ -7,6 +7,7 @@
 #include <shf_b200.h>
 
 #include <string>
+#include <vector>
 
 using namespace SuperTerrainPlus::STPAlgorithm;
 namespace STPException = SuperTerrainPlus::STPException;
@@ -122,6 +123,16 @@ STPSingleHistogram STPSingleHistogramFilter::filterBatch(const STPSample_t* cons
 	const STPGeometry geo(nn_info);
 	check(shf_run_batch(this->Filter, samplemap, chunk_count, geo.MapSize, geo.Neighbour, geo.Total, filter_buffer.Memory, radius));
 	return filter_buffer.readHistogram();
+}
+
+void STPSingleHistogramFilter::filterMulti(const STPSample_t* const* const samplemap, STPFilterBuffer* const* const filter_buffer,
+	const unsigned int call_count, const STPNearestNeighbourInformation& nn_info, const unsigned int radius) {
+	const STPGeometry geo(nn_info);
+	std::vector<shf_buffer*> memory(call_count);
+	for (unsigned int i = 0u; i < call_count; i++) {
+		memory[i] = filter_buffer[i] ? filter_buffer[i]->Memory : nullptr;
+	}
+	check(shf_run_multi(this->Filter, samplemap, memory.data(), call_count, geo.MapSize, geo.Neighbour, geo.Total, radius));
 }
 
 STPSingleHistogram STPSingleHistogramFilter::filterNeighbours(const STPSample_t* const* const neighbour_map,

@@ -33,3 +33,18 @@ def test_reference_scenario_in_cpp(shf):
     run = subprocess.run([BINARY], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "all C++ histogram checks passed" in run.stdout
+
+
+BATCHER = os.path.join(HERE, "cpp", "test_batcher")
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_through_the_batcher(shf):
+    """five worker threads, one buffer each, two geometries in flight -- every caller gets the
+    histogram a direct call gives (checked against the oracle), calls are coalesced into fewer device passes."""
+    shf.library()
+    build()
+    run = subprocess.run([BATCHER], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "all batcher checks passed" in run.stdout
+    print(run.stdout)

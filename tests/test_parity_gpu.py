@@ -247,6 +247,34 @@ def test_unmerged_neighbours_from_device_memory(shf, filt, oracle_mod):
                     oracle_mod.run_port(m, (w, h), nn, r), f"device neighbourhood {i}")
 
 
+def test_multi_call_pass_fills_every_callers_buffer(shf, filt, oracle_mod):
+    """Row f3 at the C ABI: shf_run_multi == one shf_run per (map, buffer) pair, bit for bit, including size()/type() and
+    a later ordinary call on one of the buffers."""
+    FB = shf.STPSingleHistogramFilter.STPFilterBuffer
+    rng = np.random.default_rng(4242)
+    w, h, r = 40, 28, 12
+    info = nn_info(shf, w, h)
+    kinds = ["iid", "blocky", "rare", "stripes", "hstripes"]
+    maps = [random_map(rng, w, h, 5 + 9 * i, kinds[i]) for i in range(5)]
+    bufs = [FB(FB.STPExecutionType.Parallel if i % 2 else FB.STPExecutionType.Serial) for i in range(5)]
+    hists = filt.runMulti(maps, info, bufs, r)
+    for i, (m, hist, buf) in enumerate(zip(maps, hists, bufs)):
+        want = oracle_mod.run_port(m, (w, h), (3, 3), r)
+        assert_same(split_result(hist), want, f"multi call {i}")
+        assert buf.size() == (len(want[0]), w * h + 1)
+        assert buf.type() == (FB.STPExecutionType.Parallel if i % 2 else FB.STPExecutionType.Serial)
+    # buffers stay ordinary buffers: a follower can serve a normal call next, the leader as well
+    for i in (3, 0):
+        again = split_result(filt(maps[(i + 1) % 5], info, bufs[i], r))
+        assert_same(again, oracle_mod.run_port(maps[(i + 1) % 5], (w, h), (3, 3), r), f"reuse of buffer {i}")
+    with pytest.raises(ValueError):  # one buffer cannot serve two calls of the same pass
+        filt.runMulti(maps[:2], info, [bufs[0], bufs[0]], r)
+    with pytest.raises(shf.STPNumericDomainError):
+        filt.runMulti(maps[:2], info, bufs[:2], 5)
+    for b in bufs:
+        b.close()
+
+
 def test_device_resident(shf, filt, oracle_mod):
     import torch
 

@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "blocky", "rare", "stripes"])
     ap.add_argument("--chunks", type=int, default=0, help="override the number of chunks per GPU (debugging)")
+    ap.add_argument("--radius", type=int, default=0, help="override the radius (BASELINE.json config 5 sweeps)")
+    ap.add_argument("--biomes", type=int, default=0, help="override the biome count (BASELINE.json config 5 sweeps)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU filters its own batch of the workload's size; strong: one batch is sharded")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -79,6 +81,10 @@ def workload_of(args):
     wl = dataclasses.replace(workloads.CONFIGS[args.workload], dist=args.dist)
     if args.chunks:
         wl = dataclasses.replace(wl, chunks=args.chunks)
+    if args.radius:
+        wl = dataclasses.replace(wl, radius=args.radius)
+    if args.biomes:
+        wl = dataclasses.replace(wl, biomes=args.biomes)
     return wl
 
 

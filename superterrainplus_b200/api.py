@@ -61,7 +61,8 @@ class STPUnsupportedError(STPBasic):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # SHF_LIBRARY: another build of the same library (A/B measurements of kernel variants); never a different implementation
+    return os.environ.get("SHF_LIBRARY") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None

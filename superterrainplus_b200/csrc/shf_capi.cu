@@ -189,9 +189,15 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
         const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
         const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K + 32 * 33 * 4;
-        SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-        shf::vscan_kernel<K><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
-                                                                     b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
+        if (g.TY % 8u == 0u) {
+            SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            shf::vscan_kernel<K, true><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
+                                                                               b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
+        } else {
+            SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            shf::vscan_kernel<K, false><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
+                                                                                b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
+        }
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));

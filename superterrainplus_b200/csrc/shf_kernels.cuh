@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace shf {
 
@@ -281,7 +282,7 @@ struct VscanState {
     __device__ __forceinline__ void dump(uint8_t* dst8) const { vscan_dump<K>(st, dst8); }
 };
 
-template <int K>
+template <int K, bool ALIGNED>   // ALIGNED: rows per tile (TY) is a multiple of 8
 __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint16_t* __restrict__ cmap,
                                                               uint32_t* __restrict__ cvt, uint8_t* __restrict__ base,
                                                               uint32_t* __restrict__ tmask) {
@@ -343,9 +344,11 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     // ---- output rows 1 .. H-1: row y + 2r enters, row y - 1 leaves ----
     const uint16_t* out = cmap + (size_t)n * g.PH * P + c;     // row y - 1 (leaving)
     uint32_t y = 1u;
-    if (g.TY % 8u == 0u) {
-        // groups of 8 rows ending on a multiple of 8, so that a tile's first row is always the last row of a group
-        // the samples of a group are loaded while the group before it is processed (one DRAM round trip hidden per group)
+    uint32_t next_dump = g.TY;   // the next tile's first row
+    // groups of 8 rows; the samples of a group are loaded while the group before it is processed (one DRAM round trip
+    // hidden per group). With TY a multiple of 8 a tile's first row is always the last row of a group (ALIGNED); other
+    // plans check every row.
+    {
         uint32_t n_in[8], n_out[8];
         if (y + 8u <= g.H) {
 #pragma unroll
@@ -373,15 +376,21 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
                 vs.push(ci + j, s_in[j] | (vs.enter(s_in[j], two_r + y + j) << 16));
                 vs.leave(s_out[j]);
                 vs.store_mask(mout + j * mstep);
+                if (!ALIGNED && y + j == next_dump) {
+                    if (valid) vs.dump(bout);
+                    bout += bstep;
+                    next_dump += g.TY;
+                }
             }
             ci += 8u;
             if ((ci & 31u) == 0u) vs.flush(ci - 32u);
             in += 8 * P;
             out += 8 * P;
             mout += 8 * mstep;
-            if ((y + 7u) % g.TY == 0u) {
+            if (ALIGNED && y + 7u == next_dump) {
                 if (valid) vs.dump(bout);
                 bout += bstep;
+                next_dump += g.TY;
             }
         }
     }
@@ -394,9 +403,10 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         in += P;
         out += P;
         mout += mstep;
-        if (y % g.TY == 0u) {
+        if (y == next_dump) {
             if (valid) vs.dump(bout);
             bout += bstep;
+            next_dump += g.TY;
         }
     }
     if (ci & 31u) vs.flush(ci & ~31u);

@@ -53,7 +53,7 @@ UNIT = "Mpixels/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
@@ -109,10 +109,11 @@ def config_of(wl, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; started ahead of the warm-up (nvidia-smi needs a moment
+    to come up), the samples taken inside the timed region are picked by their timestamps."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
@@ -122,7 +123,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -132,7 +133,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples stamped inside [t0, t1] (time.time() values); all samples when none falls inside."""
+        import datetime
+
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -140,22 +144,38 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        used = inside or rows
+        reasons = sorted({n for r in used for n in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in used) if used else None,
+                "sm_max_mhz": max(r[2] for r in used) if used else None, "reasons": reasons,
+                "samples": len(used), "samples_in_timed_region": len(inside)}
+
+
+def measured_traffic(kernel, wl, n_chunks):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, per chunk), scaled to the chunks of this launch; None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            table = json.load(f)
+        for row in table:
+            if (row["kernel"] == kernel and row["workload"] == wl.name and row["distribution"] == wl.dist
+                    and row["radius"] == wl.radius and row["biomes"] == wl.biomes):
+                return row["dram_bytes_per_chunk"] * n_chunks
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -307,27 +327,30 @@ def run_ours(args):
     def step():
         filt.runDevice(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     n_bins, _ = buf.size()
     plan = buf.lastPlan()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     phases = []
     api.stats_reset()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
-        phases.append(buf.phaseMs())
     e1.record()
     barrier()
+    t_wall1 = time.time()
+    # the phase events of the timed steps, read back after the timed region (no host synchronisation inside it)
+    phases = [buf.phaseMs(back) for back in range(min(args.steps, 64))]
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     launches, _, _ = api.stats()
     api.set_profiling(False)
     value = total_chunks * w * h / (ms_step * 1e-3) / 1e6
@@ -335,10 +358,10 @@ def run_ours(args):
     phases_ms = {k: statistics.median(p[k] for p in phases) for k in phases[0]}
     alg_bytes = workloads.algorithmic_bytes(wl, n_bins)
     peak, peak_src = measured_peak()
-    emit_ms = phases_ms["march_emit"]
+    emit_ms = phases_ms["emit"]
     achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "emit_kernel<K>" if plan["k_sets"] else "march_generic_kernel<emit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": measured_traffic("emit_kernel", wl, n), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
                 "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
 

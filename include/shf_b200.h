@@ -177,11 +177,14 @@ SHF_API int shf_buffer_last_plan(const shf_buffer* buffer, uint32_t* k_sets, uin
                                  uint32_t* n_biomes, uint32_t* smem_bytes);
 
 /* Measurement hook: when enabled, every call records CUDA events on its stream between the kernel phases
- * (0 dictionary, 1 remap + vertical scan, 2 counting march, 3 row scan, 4 host round trip for the bin totals,
- * 5 emitting march); shf_buffer_phase_ms waits for
- * the last call on the buffer and returns the milliseconds of the first n phases. */
+ * (0 dictionary, 1 remap + vertical scan, 2 event lists (wide path: counting pass), 3 row scan, 4 host round trip for
+ * the bin totals, 5 emit); shf_buffer_phase_ms waits for the last call on the buffer and returns the milliseconds of
+ * the first n phases. */
 SHF_API void shf_set_profiling(int enabled);
 SHF_API int shf_buffer_phase_ms(const shf_buffer* buffer, float* ms, uint32_t n);
+/* Same for the call `back` calls before the last one (0 = the last; the events of the last 64 profiled calls are kept),
+ * so that a timed loop can be read back afterwards without a host synchronisation per call. */
+SHF_API int shf_buffer_phase_history(const shf_buffer* buffer, uint32_t back, float* ms, uint32_t n);
 
 #ifdef __cplusplus
 }

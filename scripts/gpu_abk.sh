@@ -9,7 +9,7 @@ for v in "--workload C3 --dist uniform" "--workload C3 --dist blocky" "--workloa
 import json
 try:
     d=json.load(open("gpurun_out/ab.json"))
-    print("$(basename $lib) | $v | %.0f Mpx/s step %.3f ms emit %.3f events %.3f vscan %.3f bins/px %.2f K=%s" % (d["value"], d["ms_per_step"], d["phases_ms"]["march_emit"], d["phases_ms"]["rowcount"], d["phases_ms"]["remap_vscan"], d["config"]["bins_per_pixel"], d["config"]["plan"]["k_sets"]))
+    print("$(basename $lib) | $v | %.0f Mpx/s step %.3f ms emit %.3f events %.3f vscan %.3f bins/px %.2f K=%s" % (d["value"], d["ms_per_step"], d["phases_ms"]["emit"], d["phases_ms"]["events"], d["phases_ms"]["remap_vscan"], d["config"]["bins_per_pixel"], d["config"]["plan"]["k_sets"]))
 except Exception as e:
     print("$(basename $lib) | $v | failed", e); print(open("gpurun_out/ab.err").read()[-400:])
 PY

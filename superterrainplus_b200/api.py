@@ -35,9 +35,9 @@ C_ABI_SYMBOLS = (
     "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_run_neighbours",
     "shf_run_neighbours_device", "shf_run_multi", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
-    "shf_set_profiling", "shf_buffer_phase_ms", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
+    "shf_set_profiling", "shf_buffer_phase_ms", "shf_buffer_phase_history", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
 )
-PHASES = ("dictionary", "remap_vscan", "rowcount", "rowscan", "host_gap", "march_emit")
+PHASES = ("dictionary", "remap_vscan", "events", "rowscan", "host_gap", "emit")
 
 
 class STPBasic(Exception):
@@ -107,6 +107,7 @@ def library() -> ctypes.CDLL:
     lib.shf_set_profiling.argtypes = [ctypes.c_int]
     lib.shf_set_profiling.restype = None
     lib.shf_buffer_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
+    lib.shf_buffer_phase_history.argtypes = [vp, u32, P(ctypes.c_float), u32]
     lib.shf_heightfield_create.argtypes = [P(vp), vp, vp, u32, vp, vp, u32]
     lib.shf_heightfield_destroy.argtypes = [vp]
     lib.shf_heightfield_destroy.restype = None
@@ -230,10 +231,11 @@ class STPSingleHistogramFilter:
                 return np.zeros(0, dtype=np.uint64)
             return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), (n.value + 1,)).copy()
 
-        def phaseMs(self) -> dict:
-            """Milliseconds of every kernel phase of the last call (needs set_profiling(True) before the call)."""
+        def phaseMs(self, back: int = 0) -> dict:
+            """Milliseconds of every kernel phase of the last call, or of the call `back` calls before it (the last 64
+            profiled calls are kept; needs set_profiling(True) before the calls)."""
             ms = (ctypes.c_float * len(PHASES))()
-            _check(library().shf_buffer_phase_ms(self._h, ms, len(PHASES)))
+            _check(library().shf_buffer_phase_history(self._h, back, ms, len(PHASES)))
             return dict(zip(PHASES, [float(v) for v in ms]))
 
         def lastPlan(self) -> dict:

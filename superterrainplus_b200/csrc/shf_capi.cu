@@ -20,7 +20,8 @@ namespace {
 thread_local std::string tls_error;
 thread_local uint64_t tls_launches = 0, tls_h2d = 0, tls_d2h = 0;
 volatile int g_profiling = 0;  // shf_set_profiling: record CUDA events between the kernel phases
-constexpr int kPhases = 6;     // dictionary | remap + vscan | counting march | row scan | host gap | emitting march
+constexpr int kEvRing = 64;    // profiled calls whose phase events are kept per buffer (read back without a sync per call)
+constexpr int kPhases = 6;     // dictionary | remap + vscan | event lists | row scan | host gap | emit
 
 int fail(int status, const char* expr, const std::string& what) {
     tls_error = std::string(expr) + ": " + what;
@@ -115,22 +116,27 @@ struct shf_buffer {
     bool has_result = false, on_host = false;
     bool dev_valid = false;  // the device arrays hold this buffer's result (not so for the followers of shf_run_multi)
     uint32_t plan_k = 0, plan_ty = 0, plan_biomes = 0, plan_smem = 0;
-    cudaEvent_t ev[kPhases + 1] = {};
+    cudaEvent_t ev[kEvRing][kPhases + 1] = {};
+    uint64_t ev_calls = 0;   // profiled calls so far; call c uses ring slot c % kEvRing
     bool ev_valid = false;
     cudaError_t mark(int i, cudaStream_t s) {
         if (!g_profiling) return cudaSuccess;
-        if (!ev[i]) {
-            const cudaError_t e = cudaEventCreate(&ev[i]);
-            if (e != cudaSuccess) return e;
+        if (i == 0) ev_calls++;
+        cudaEvent_t& e = ev[(ev_calls - 1u) % kEvRing][i];
+        if (!e) {
+            const cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
         }
-        return cudaEventRecord(ev[i], s);
+        return cudaEventRecord(e, s);
     }
     void release_all() {
-        for (cudaEvent_t& e : ev) {
-            if (e) cudaEventDestroy(e);
-            e = nullptr;
-        }
+        for (auto& set : ev)
+            for (cudaEvent_t& e : set) {
+                if (e) cudaEventDestroy(e);
+                e = nullptr;
+            }
         ev_valid = false;
+        ev_calls = 0;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
                        &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
                        &evpool, &rowinfo, &cvt};
@@ -858,13 +864,20 @@ void shf_stats_get(uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h
 
 void shf_set_profiling(int enabled) { g_profiling = enabled ? 1 : 0; }
 
-int shf_buffer_phase_ms(const shf_buffer* b, float* ms, uint32_t n) {
+int shf_buffer_phase_history(const shf_buffer* b, uint32_t back, float* ms, uint32_t n) {
     if (!b || !ms) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
     if (!b->ev_valid) return fail(SHF_ERR_INVALID_ARGUMENT, "profiling enabled", "no phase events recorded for the last call");
-    SHF_CUDA(cudaEventSynchronize(b->ev[kPhases]));
-    for (uint32_t i = 0; i < n && i < (uint32_t)kPhases; i++) SHF_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    if (back >= (uint32_t)kEvRing || back >= b->ev_calls)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "back < profiled calls kept", "no phase events kept that far back");
+    const cudaEvent_t* set = b->ev[(b->ev_calls - 1u - back) % kEvRing];
+    for (int i = 0; i <= kPhases; i++)
+        if (!set[i]) return fail(SHF_ERR_INVALID_ARGUMENT, "all phases recorded", "that call did not run every phase");
+    SHF_CUDA(cudaEventSynchronize(set[kPhases]));
+    for (uint32_t i = 0; i < n && i < (uint32_t)kPhases; i++) SHF_CUDA(cudaEventElapsedTime(&ms[i], set[i], set[i + 1]));
     return SHF_OK;
 }
+
+int shf_buffer_phase_ms(const shf_buffer* b, float* ms, uint32_t n) { return shf_buffer_phase_history(b, 0u, ms, n); }
 
 int shf_buffer_last_plan(const shf_buffer* b, uint32_t* k_sets, uint32_t* rows_per_cta, uint32_t* n_biomes,
                          uint32_t* smem_bytes) {

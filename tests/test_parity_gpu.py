@@ -181,6 +181,23 @@ def test_batch_matches_single(shf, filt, oracle_mod):
     buf.close()
 
 
+SWEEP = [(r, b, kind) for r in (8, 16, 32, 64, 128) for b in (4, 16, 64, 256, 1024) for kind in ("iid", "blocky")]
+
+
+@pytest.mark.parametrize("r,biomes,kind", SWEEP)
+def test_config5_radius_biome_sweep(shf, filt, oracle_mod, r, biomes, kind):
+    """BASELINE.json config 5: radius 8-128 x biome count 4-1024, dense (iid) and sparse (blocky) histograms, on maps the
+    oracle finishes in well under a second; both the register-list path and the wide path are crossed."""
+    w, h = 72, 40
+    nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
+    rng = np.random.default_rng(r * 4099 + biomes)
+    m = random_map(rng, w, h, biomes, kind, nn)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+    assert_same(got, oracle_mod.run_port(m, (w, h), nn, r), f"sweep r={r} B={biomes} {kind}")
+    buf.close()
+
+
 def split_neighbours(m, w, h, nn):
     """The nn.x * nn.y chunk maps of a merged map, in local-index order (STPChunk::calcLocalChunkCoordinate)."""
     return [np.ascontiguousarray(m[cy * h:(cy + 1) * h, cx * w:(cx + 1) * w]) for cy in range(nn[1]) for cx in range(nn[0])]

@@ -265,6 +265,22 @@ struct VscanState {
         st[o * kVscanThreads] = w;
         if ((w & 0xFFFFu) == 0u) atomicAnd(&tm[o], ~lanebit);
     }
+    // row p enters and the row 2r+1 above it leaves, in one go: both state words are loaded together (one shared-memory
+    // round trip instead of two). When both rows hold the same value nothing changes: its count is >= 1 already (the
+    // leaving row is inside the window), so no chain starts, and +1 -1 cancel.
+    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t o, uint32_t p) {
+        uint32_t ws = st[s * kVscanThreads], wo = st[o * kVscanThreads];
+        const bool born = (ws & 0xFFFFu) == 0u;
+        ws = born ? p << 16 : ws;
+        if (s != o) {
+            st[s * kVscanThreads] = ws + 1u;
+            wo -= 1u;
+            st[o * kVscanThreads] = wo;
+            if (born) atomicOr(&tm[s], lanebit);
+            if ((wo & 0xFFFFu) == 0u) atomicAnd(&tm[o], ~lanebit);
+        }
+        return ws >> 16;
+    }
     __device__ __forceinline__ void store_mask(uint32_t* dst) const {
         __syncwarp();
 #pragma unroll
@@ -373,8 +389,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                vs.push(ci + j, s_in[j] | (vs.enter(s_in[j], two_r + y + j) << 16));
-                vs.leave(s_out[j]);
+                vs.push(ci + j, s_in[j] | (vs.step(s_in[j], s_out[j], two_r + y + j) << 16));
                 vs.store_mask(mout + j * mstep);
                 if (!ALIGNED && y + j == next_dump) {
                     if (valid) vs.dump(bout);
@@ -396,9 +411,8 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     }
     for (; y < g.H; y++) {
         const uint32_t sv = *in;
-        vs.push(ci, sv | (vs.enter(sv, two_r + y) << 16));
+        vs.push(ci, sv | (vs.step(sv, *out, two_r + y) << 16));
         if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
-        vs.leave(*out);
         vs.store_mask(mout);
         in += P;
         out += P;

@@ -435,10 +435,11 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
         if (smem_of(ty) > f->smem_optin) plan(1u, 1u);
         while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
-        // small calls: fewer rows per CTA until the grid covers the SMs (a single 512x512 chunk has 32 tiles of 16 rows)
+        // small calls: 8 rows per CTA when 16 would leave more than half of the SMs idle (a single 512x512 chunk has 32
+        // tiles of 16 rows: emit 0.054 -> 0.046 ms; a 2048x2048 chunk with its 128 tiles is better off with 16)
         // (8, not fewer: vscan dumps a base vector per tile and its fast variant wants multiples of 8)
         if (const char* e = getenv("SHF_DEBUG_TY")) ty = std::max(1u, std::min(ty, (uint32_t)atoi(e)));  // measurements only
-        else if (ty > 8u && (uint64_t)n_chunks * ((H + ty - 1u) / ty) < (uint64_t)f->sm_count) ty = 8u;
+        else if (ty > 8u && (uint64_t)n_chunks * ((H + ty - 1u) / ty) * 2u <= (uint64_t)f->sm_count) ty = 8u;
         if (smem_of(ty) > f->smem_optin) {
             generic = true;
             g.Bpad = (bmax + 31u) & ~31u;

@@ -446,8 +446,16 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         barrier()
         dt = max_over_ranks(dt / args.e2e_steps)
+        # bytes of the whole job: every rank moves its own share
+        if world > 1:
+            tb = torch.tensor([sum(m[1] for m in moved), sum(m[2] for m in moved)], dtype=torch.float64,
+                              device="cuda" if args.backend == "nccl" else "cpu")
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+            h2d_total, d2h_total = int(tb[0].item()), int(tb[1].item())
+        else:
+            h2d_total, d2h_total = sum(m[1] for m in moved), sum(m[2] for m in moved)
         e2e = {"value": total_chunks * w * h / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": sum(m[1] for m in moved), "d2h_bytes_per_step": sum(m[2] for m in moved),
+               "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "how": f"shf_run_batch on pinned host maps, {sub} chunks per call, {n_threads} host threads with one "
                       "filter buffer each; bins + offsets copied to page-locked host memory inside the timed region",

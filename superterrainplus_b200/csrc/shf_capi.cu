@@ -376,7 +376,6 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     g.in_row_stride = in_row_stride;
     g.in_chunk_stride = in_chunk_stride;
     g.inv_total = 1.0f / (float)(g.span * g.span);
-    if (const char* e = getenv("SHF_DEBUG_FLAGS")) g.flags = (uint32_t)atoi(e);  // measurement toggles only
     if (W == 0u || H == 0u || n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "W*H*n_chunks > 0", "empty input");
     if (n_chunks > 65535u) return fail(SHF_ERR_UNSUPPORTED, "n_chunks <= 65535", "too many chunks in one batch");
     if (g.PH >= 65535u) return fail(SHF_ERR_UNSUPPORTED, "H + 2*radius < 65535", "map too tall for 16-bit row keys");

@@ -36,16 +36,14 @@ struct Geo {
     uint32_t n_chunks;
     uint32_t in_row_stride;        // input view: sample(n,p,c) = in[n*in_chunk_stride + p*in_row_stride + c]
     uint64_t in_chunk_stride;
-    uint32_t TY, T;                // rows per march CTA, tiles per chunk
+    uint32_t TY, T;                // rows per emit CTA, tiles per chunk
     uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
     uint32_t R;                    // ring columns = span + 16 * stages
-    uint32_t stages;               // batches the march producers may run ahead of the consumers (2..6)
-    uint32_t producers;            // producer warps of the march kernel (1..4)
+    uint32_t stages;               // batches the emit producers may run ahead of the consumers (2..6)
+    uint32_t producers;            // producer warps of the emit kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
-    uint32_t flags;                // bit 0: do not use the packed short-list path (A/B measurements)
-    unsigned long long* dbg;       // measurement only: cycle counters of the march kernel, or null
 };
 
 // ------------------------------------------------------------------------------------------------------------------

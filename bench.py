@@ -276,6 +276,40 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """One rank per GPU: run this rank's host threads (and first-touch its page-locked buffers) on the NUMA node its GPU
+    hangs off, so that the end-to-end leg's 34 GB of histograms per rank and step do not cross the socket interconnect.
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local).pci_bus_id  # available in recent torch; else nvidia-smi below
+    except Exception:
+        bus = None
+    try:
+        if not isinstance(bus, str) or ":" not in bus:
+            q = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                               capture_output=True, text=True, timeout=20).stdout.strip()
+            bus = q
+        dom, b, rest = bus.lower().split(":")
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{b}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -289,6 +323,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the filter has no CPU path (use --impl reference for the CPU filter)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if args.backend == "nccl":
@@ -476,6 +511,7 @@ def run_ours(args):
             "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic",
             "config": {**config_of(wl, world), "plan": plan, "bins_per_pixel": n_bins / (n * w * h)},
             "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e, "consumer": consumer,
+            "host_numa_node_rank0": numa,
             "gpu_launches": launches, "clocks": clocks, "impl": "ours",
         }
         emit(line)

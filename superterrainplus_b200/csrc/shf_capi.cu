@@ -160,11 +160,11 @@ uint32_t shf_rows_grid(uint32_t PH, uint32_t n_chunks) {
     return std::max(1u, std::min(std::min(want, PH), 256u));
 }
 
-size_t emit_smem(uint32_t ty, uint32_t R, int K) {
-    return (size_t)ty * R * 32 * K + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K) + (size_t)ty * shf::emit_act_cap(K) * 8 + 128 +
+size_t emit_smem(uint32_t ty, uint32_t R, int K, int FW) {
+    return (size_t)ty * R * 32 * K * FW / 8 + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K, FW) +
+           (size_t)ty * shf::emit_act_cap(K) * 8 + 128 +
            4 * 1024;  // barriers + the producers' sample scratch (<= 1 KB per producer warp)
 }
-
 
 template <int K>
 int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
@@ -209,11 +209,20 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         SHF_CUDA(b->mark(2, s));
         return launch_events<K>(b, g, s);
     }
-    const size_t smem = emit_smem(g.TY, g.R, K);
-    SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shf::emit_kernel<K><<<dim3(g.T, g.n_chunks), (g.TY + g.producers) * 32, smem, s>>>(
-        g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
-        b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
+    const size_t smem = emit_smem(g.TY, g.R, K, (int)g.FW);
+    const dim3 grid(g.T, g.n_chunks);
+    const uint32_t threads = (g.TY + g.producers) * 32;
+    if (g.FW == 8u) {
+        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::emit_kernel<K, 8><<<grid, threads, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+            b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
+    } else {
+        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shf::emit_kernel<K, 16><<<grid, threads, smem, s>>>(
+            g, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+            b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
+    }
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
     return SHF_OK;
@@ -410,25 +419,26 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     uint32_t bmax = 0;
     for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
     if (bmax > 65535u) return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 65535", "compact ids are 16 bits wide");
-    // The register-list march covers up to 256 distinct values and 8-bit vertical window counts (2r+1 <= 255) as long
-    // as one row's ring fits shared memory; everything else takes the wide path of shf_generic.cuh.
     const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
     g.K = K;
     g.Bpad = (bmax + 31u) & ~31u;
-    bool generic = bmax > 256u || g.span > 255u;
+    // The event-list path covers up to 256 distinct values and 2r+1 <= 511 (8-bit vertical window counts up to 255,
+    // 16-bit ones beyond) as long as one row's ring fits shared memory; everything else takes the wide path.
+    g.FW = g.span <= 255u ? 8u : 16u;
+    bool generic = bmax > 256u || g.span > 511u;
     if (!generic) {
         g.Bpad = 32u * K;
         // march kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
         // `ppb` passes; with `np` producer warps ceil(np / ppb) batches are in production at once, and the ring must
         // hold one more batch than that besides the 2r+1 columns the consumers still read.
-        const uint32_t ppb = K == 1 ? 1u : K == 2 ? 2u : K == 4 ? 4u : 8u;
+        const uint32_t ppb = (uint32_t)K * g.FW / 8u;
         uint32_t ty = std::min<uint32_t>(16u, H);
         auto plan = [&](uint32_t np, uint32_t extra) {
             g.producers = np;
             g.stages = (np + ppb - 1u) / ppb + extra;
             g.R = g.span + shf::kMarchNB * g.stages;
         };
-        auto smem_of = [&](uint32_t t) { return emit_smem(t, g.R, K); };
+        auto smem_of = [&](uint32_t t) { return emit_smem(t, g.R, K, (int)g.FW); };
         plan(4u, 2u);
         if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
         if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
@@ -453,7 +463,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     b->plan_biomes = bmax;
     if (generic) return run_generic(f, b, g, in_dev, vec8, bmax, h_totals, s);
 
-    SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad));
+    SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad * g.FW / 8u));
     SHF_CUDA(b->colmask.ensure((size_t)n_chunks * H * ((g.PW + 31u) / 32u) * 32u * K * 4));  // transposed masks per 32-column block
     {
         g.cv_pad = (32u - g.span % 32u) % 32u;

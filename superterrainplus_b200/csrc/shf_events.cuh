@@ -124,17 +124,19 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
             if (gsz > 1u) {
                 // order them by the start row of their vertical chain: every cell of the column's window publishes the
                 // chain start of its value (all cells of one value inside a window agree)
-                // (2r+1 <= 255 on this path: 8 cells per lane at most; all loads go out before the first store)
-                uint32_t cell[8];
+                // (2r+1 <= 511 on this path: two rounds of 8 cells per lane; the loads of a round go out before its stores)
                 const uint32_t* colw = cv + (size_t)c * g.cv_pitch + g.cv_pad + y;  // the column's window, contiguous
+                for (uint32_t o0 = 0u; o0 < span; o0 += 256u) {
+                    uint32_t cell[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint32_t o = lane + 32u * (uint32_t)i;
-                    if (o < span) cell[i] = colw[o];
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t o = o0 + lane + 32u * (uint32_t)i;
+                        if (o < span) cell[i] = colw[o];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (o0 + lane + 32u * (uint32_t)i < span) tab[cell[i] & 0xFFFFu] = (uint16_t)(cell[i] >> 16);
                 }
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (lane + 32u * (uint32_t)i < span) tab[cell[i] & 0xFFFFu] = (uint16_t)(cell[i] >> 16);
                 __syncwarp();
                 uint32_t vk[K];
 #pragma unroll
@@ -237,75 +239,103 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
 // ------------------------------------------------------------------------------------------------------------------
 // emit: producers as in march_kernel (vertical window counts into a shared-memory ring), consumers = one warp per row
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K) { return 64u * (uint32_t)K + (K <= 2 ? 4u : 2u * (uint32_t)K); }
+// FW = bits per vertical window count in the ring: 8 while 2r+1 <= 255, else 16 (2r+1 <= 511; the horizontal window
+// counts then need 32 bits: (2r+1)^2 exceeds 65535 from r = 128 on).
+__host__ __device__ constexpr uint32_t emit_sbuf_stride(int K, int FW = 8) {
+    return FW == 8 ? 64u * (uint32_t)K + (K <= 2 ? 4u : 2u * (uint32_t)K) : 128u * (uint32_t)K + 4u * (uint32_t)K;
+}
 __host__ __device__ constexpr uint32_t emit_act_cap(int K) { return 32u * (uint32_t)K + 32u; }
+__host__ __device__ constexpr int emit_acc_regs(int K, int FW) { return FW == 8 ? (K + 1) / 2 : K; }
 
-// K bytes of one count vector (compact ids lane*K .. lane*K+K-1) widened to 16-bit pairs
-template <int K>
-__device__ __forceinline__ void load_counts(const uint8_t* p, uint32_t (&v)[(K + 1) / 2]) {
-    if (K == 1) {
-        v[0] = *p;
-    } else if (K == 2) {
-        const uint32_t t = *reinterpret_cast<const uint16_t*>(p);
-        v[0] = __byte_perm(t, 0u, 0x4140);
-    } else if (K == 4) {
-        const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
-        v[0] = __byte_perm(t, 0u, 0x4140);
-        v[1] = __byte_perm(t, 0u, 0x4342);
+// The K counts of one count vector a lane owns (compact ids lane*K .. lane*K+K-1): 8-bit counts widened to 16-bit
+// pairs, 16-bit counts to one 32-bit word each
+template <int K, int FW>
+__device__ __forceinline__ void load_counts(const uint8_t* p, uint32_t (&v)[emit_acc_regs(K, FW)]) {
+    if (FW == 8) {
+        if (K == 1) {
+            v[0] = *p;
+        } else if (K == 2) {
+            const uint32_t t = *reinterpret_cast<const uint16_t*>(p);
+            v[0] = __byte_perm(t, 0u, 0x4140);
+        } else if (K == 4) {
+            const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+            v[0] = __byte_perm(t, 0u, 0x4140);
+            v[1 % emit_acc_regs(K, FW)] = __byte_perm(t, 0u, 0x4342);
+        } else {
+            const uint2 t = *reinterpret_cast<const uint2*>(p);
+            v[0] = __byte_perm(t.x, 0u, 0x4140);
+            v[1 % emit_acc_regs(K, FW)] = __byte_perm(t.x, 0u, 0x4342);
+            v[2 % emit_acc_regs(K, FW)] = __byte_perm(t.y, 0u, 0x4140);
+            v[3 % emit_acc_regs(K, FW)] = __byte_perm(t.y, 0u, 0x4342);
+        }
     } else {
-        const uint2 t = *reinterpret_cast<const uint2*>(p);
-        v[0] = __byte_perm(t.x, 0u, 0x4140);
-        v[1] = __byte_perm(t.x, 0u, 0x4342);
-        v[2] = __byte_perm(t.y, 0u, 0x4140);
-        v[3] = __byte_perm(t.y, 0u, 0x4342);
+        if (K == 1) {
+            v[0] = *reinterpret_cast<const uint16_t*>(p);
+        } else if (K == 2) {
+            const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+            v[0] = t & 0xFFFFu;
+            v[1 % K] = t >> 16;
+        } else {
+#pragma unroll
+            for (int q = 0; q < K / 4; q++) {
+                const uint2 t = reinterpret_cast<const uint2*>(p)[q];
+                v[(4 * q) % K] = t.x & 0xFFFFu;
+                v[(4 * q + 1) % K] = t.x >> 16;
+                v[(4 * q + 2) % K] = t.y & 0xFFFFu;
+                v[(4 * q + 3) % K] = t.y >> 16;
+            }
+        }
     }
 }
 
-template <int K>
-__device__ __forceinline__ void store_sums(uint8_t* p, const uint32_t (&v)[(K + 1) / 2]) {
-    if (K == 1) {
-        *reinterpret_cast<uint16_t*>(p) = (uint16_t)v[0];
-    } else if (K == 2) {
-        *reinterpret_cast<uint32_t*>(p) = v[0];
-    } else if (K == 4) {
-        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+template <int K, int FW>
+__device__ __forceinline__ void store_sums(uint8_t* p, const uint32_t (&v)[emit_acc_regs(K, FW)]) {
+    constexpr int N = emit_acc_regs(K, FW);
+    if (N == 1) {
+        if (FW == 8 && K == 1) *reinterpret_cast<uint16_t*>(p) = (uint16_t)v[0];
+        else *reinterpret_cast<uint32_t*>(p) = v[0];
+    } else if (N == 2) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1 % N]);
     } else {
-        *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int q = 0; q < N / 4; q++)
+            reinterpret_cast<uint4*>(p)[q] = make_uint4(v[(4 * q) % N], v[(4 * q + 1) % N], v[(4 * q + 2) % N], v[(4 * q + 3) % N]);
     }
 }
 
 // n columns of the dense horizontal slide: srun += counts(column c) - counts(column c - span); the window counts of a
 // pixel (c >= 2r) go to the staging rows. OUT: the leaving column exists; ST: store.
-template <int K, bool OUT, bool ST>
+template <int K, int FW, bool OUT, bool ST>
 __device__ __forceinline__ void slide_cols(const uint8_t* pin, const uint8_t* pout, uint8_t* ps, uint32_t n,
-                                           uint32_t (&srun)[(K + 1) / 2]) {
-    constexpr int CS = 32 * K, SR = (K + 1) / 2;
-    constexpr uint32_t SS = emit_sbuf_stride(K);
-    while (n >= 4u) {
-        uint32_t a[4][SR], o[4][SR];
+                                           uint32_t (&srun)[emit_acc_regs(K, FW)]) {
+    constexpr int CS = 32 * K * FW / 8, SR = emit_acc_regs(K, FW);
+    constexpr uint32_t SS = emit_sbuf_stride(K, FW);
+    constexpr int UJ = SR <= 4 ? 4 : 2;
+    while (n >= (uint32_t)UJ) {
+        uint32_t a[UJ][SR], o[UJ][SR];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            load_counts<K>(pin + j * CS, a[j]);
-            if (OUT) load_counts<K>(pout + j * CS, o[j]);
+        for (int j = 0; j < UJ; j++) {
+            load_counts<K, FW>(pin + j * CS, a[j]);
+            if (OUT) load_counts<K, FW>(pout + j * CS, o[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < UJ; j++) {
 #pragma unroll
             for (int i = 0; i < SR; i++) srun[i] = OUT ? srun[i] + a[j][i] - o[j][i] : srun[i] + a[j][i];
-            if (ST) store_sums<K>(ps + j * SS, srun);
+            if (ST) store_sums<K, FW>(ps + j * SS, srun);
         }
-        pin += 4 * CS;
-        pout += 4 * CS;
-        ps += 4 * SS;
-        n -= 4u;
+        pin += UJ * CS;
+        pout += UJ * CS;
+        ps += UJ * SS;
+        n -= (uint32_t)UJ;
     }
     while (n) {
         uint32_t a[SR], o[SR];
-        load_counts<K>(pin, a);
-        if (OUT) load_counts<K>(pout, o);
+        load_counts<K, FW>(pin, a);
+        if (OUT) load_counts<K, FW>(pout, o);
 #pragma unroll
         for (int i = 0; i < SR; i++) srun[i] = OUT ? srun[i] + a[i] - o[i] : srun[i] + a[i];
-        if (ST) store_sums<K>(ps, srun);
+        if (ST) store_sums<K, FW>(ps, srun);
         pin += CS;
         pout += CS;
         ps += SS;
@@ -313,23 +343,32 @@ __device__ __forceinline__ void slide_cols(const uint8_t* pin, const uint8_t* po
     }
 }
 
+// window count of compact id `id` in a staging row
+template <int FW>
+__device__ __forceinline__ uint32_t staged_count(uint32_t row_addr, uint32_t id) {
+    uint32_t c;
+    if (FW == 8) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c) : "r"(row_addr + id * 2u));
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(row_addr + id * 4u));
+    return c;
+}
+
 // shared memory of an emit CTA:
-//   cring[TY][R][32K]  u8   vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
-//   sbuf[TY][16][SS]   u16  horizontal window counts of the batch being emitted, SS = 64K + pad bytes per pixel
+//   cring[TY][R][32K]  u8 / u16  vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
+//   sbuf[TY][16][SS]   u16 / u32 horizontal window counts of the batch being emitted, SS bytes per pixel
 //   act[TY][32K+32]    8 B  the events overlapping the pixels being emitted, in list order
 
-template <int K>
+template <int K, int FW>
 __global__ void __launch_bounds__(640, 1)
     emit_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint8_t* __restrict__ base,
                 const uint2* __restrict__ pool, const uint2* __restrict__ rowinfo, const uint32_t* __restrict__ rowbase,
                 const uint64_t* __restrict__ chunkbase, uint2* __restrict__ bins, uint32_t* __restrict__ hso) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int CS = 32 * K;
+    constexpr int CS = 32 * K * FW / 8;            // bytes of one count vector
     constexpr int NB = kMarchNB;
     constexpr int KE = K + 1;                      // register sets of the active list
-    constexpr uint32_t SS = emit_sbuf_stride(K);
+    constexpr uint32_t SS = emit_sbuf_stride(K, FW);
     constexpr uint32_t ACAP = emit_act_cap(K);
-    constexpr int SR = (K + 1) / 2;
+    constexpr int SR = emit_acc_regs(K, FW);
     const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW, stages = g.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
@@ -344,7 +383,7 @@ __global__ void __launch_bounds__(640, 1)
     uint64_t* empty_bar = full_bar + 8;
     uint8_t* pscr_all = reinterpret_cast<uint8_t*>(empty_bar + 8);  // [producers][2][CPP][16] u16
     if (threadIdx.x < stages) {
-        mbar_init(&full_bar[threadIdx.x], (uint32_t)(NB / (32 / (2 * K))));
+        mbar_init(&full_bar[threadIdx.x], (uint32_t)(NB / (32 / (CS / 16))));  // producer passes per batch
         mbar_init(&empty_bar[threadIdx.x], TY);
     }
     __syncthreads();
@@ -355,10 +394,10 @@ __global__ void __launch_bounds__(640, 1)
         // Work item t = (batch b, pass q): CPP columns x the tile's rows. The samples entering / leaving the vertical
         // window (rows y0+i+span and y0+i) are fetched as one row segment per lane (lanes 0-15 entering, 16-31
         // leaving), a whole item ahead of their use, and handed to the column lanes through a transposed scratch.
-        constexpr int LPC = 2 * K;       // lanes per column, 16 bytes of counters each
+        constexpr int LPC = CS / 16;     // lanes per column, 16 bytes of counters each
         constexpr int CPP = 32 / LPC;    // columns per pass
         constexpr int PPB = NB / CPP;    // passes per batch
-        constexpr int SW = CPP / 2;      // 32-bit words of one row segment
+        constexpr int SW = CPP > 1 ? CPP / 2 : 1;  // 32-bit words of one row segment (one 16-bit sample when CPP = 1)
         const uint32_t part = lane % LPC, colq = lane / LPC;
         const uint32_t tile_rows = min(TY, g.H - y0);
         const uint32_t bit0 = part * 128u;
@@ -382,8 +421,10 @@ __global__ void __launch_bounds__(640, 1)
             } else if (SW == 2) {
                 const uint2 a = reinterpret_cast<const uint2*>(src)[0];
                 seg_n[0] = a.x, seg_n[1 % SW] = a.y;
-            } else {
+            } else if (CPP == 2) {
                 seg_n[0] = src[0];
+            } else {
+                seg_n[0] = seg_row[c0];
             }
             const uint32_t c = min(c0 + colq, PW - 1u);
             v_n = *reinterpret_cast<const uint4*>(base_tile + (size_t)c * CS);
@@ -419,11 +460,11 @@ __global__ void __launch_bounds__(640, 1)
                 if ((uint32_t)i < tile_rows) {
                     if (live) *reinterpret_cast<uint4*>(out) = v;
                     out += (size_t)R * CS;
-                    // counter of compact id a sits at bit 8a of the column vector; a shift by >= 32 (or "negative",
+                    // counter of compact id a sits at bit FW*a of the column vector; a shift by >= 32 (or "negative",
                     // i.e. huge) yields 0 with PTX shl, so every word only sees its own counters
                     const uint32_t sa = (i & 1) ? wa[i / 2] >> 16 : wa[i / 2] & 0xFFFFu;
                     const uint32_t so = (i & 1) ? wo[i / 2] >> 16 : wo[i / 2] & 0xFFFFu;
-                    const uint32_t ba = sa * 8u - bit0, bo = so * 8u - bit0;
+                    const uint32_t ba = sa * (uint32_t)FW - bit0, bo = so * (uint32_t)FW - bit0;
                     v.x += shl_clamp(1u, ba) - shl_clamp(1u, bo);
                     v.y += shl_clamp(1u, ba - 32u) - shl_clamp(1u, bo - 32u);
                     v.z += shl_clamp(1u, ba - 64u) - shl_clamp(1u, bo - 64u);
@@ -478,12 +519,12 @@ __global__ void __launch_bounds__(640, 1)
                 seg_end = has_out ? min(seg_end, c + (R - out_slot)) : min(seg_end, span);
                 if (!st) seg_end = min(seg_end, two_r);
                 const uint32_t n = seg_end - c;
-                const uint8_t* pin = crow + in_slot * CS + lane * K;
-                const uint8_t* pout = crow + out_slot * CS + lane * K;
-                uint8_t* ps = sb + (c - cb) * SS + lane * (2 * K);
-                if (has_out) slide_cols<K, true, true>(pin, pout, ps, n, srun);
-                else if (st) slide_cols<K, false, true>(pin, pout, ps, n, srun);
-                else slide_cols<K, false, false>(pin, pout, ps, n, srun);
+                const uint8_t* pin = crow + in_slot * CS + lane * (K * FW / 8);
+                const uint8_t* pout = crow + out_slot * CS + lane * (K * FW / 8);
+                uint8_t* ps = sb + (c - cb) * SS + lane * (FW == 8 ? 2 * K : 4 * K);
+                if (has_out) slide_cols<K, FW, true, true>(pin, pout, ps, n, srun);
+                else if (st) slide_cols<K, FW, false, true>(pin, pout, ps, n, srun);
+                else slide_cols<K, FW, false, false>(pin, pout, ps, n, srun);
                 in_slot += n;
                 if (in_slot >= R) in_slot -= R;
                 out_slot += n;
@@ -560,7 +601,8 @@ __global__ void __launch_bounds__(640, 1)
                         const uint32_t len = lim > xb ? lim - xb : 0u;             // alive <=> (x - xb) < len
                         const uint32_t hlim = (pk_entry == 0u && pk_slot < pk_n) ? xe : 0u;  // this lane stores the offset of x
                         uint32_t x = xa + pk_slot;
-                        uint32_t sa = smem_addr(sp) + pk_slot * SS + (rx[0] & 0xFFFFu) * 2u;
+                        uint32_t sa = smem_addr(sp) + pk_slot * SS;
+                        const uint32_t vid = rx[0] & 0xFFFFu;
                         const uint32_t sa_step = pk_n * SS;
                         uint32_t* hp = hso_row + x;
                         for (uint32_t xp = xa; xp < xe; xp += pk_n) {
@@ -568,8 +610,7 @@ __global__ void __launch_bounds__(640, 1)
                             const unsigned bm = __ballot_sync(kFull, alive);
                             const uint32_t pos = (uint32_t)__popc(bm & lanemask_lt());
                             if (alive) {
-                                uint32_t cnt;
-                                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(cnt) : "r"(sa));
+                                const uint32_t cnt = staged_count<FW>(sa, vid);
                                 dst[pos] = make_uint2(itm, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
                             }
                             if (x < hlim) *hp = off + pos;
@@ -588,7 +629,7 @@ __global__ void __launch_bounds__(640, 1)
                                 if ((uint32_t)(k * 32) < Ea) {
                                     const uint32_t idx = k * 32 + lane;
                                     if (idx < Ea) {
-                                        const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (rx[k] & 0xFFFFu) * 2u);
+                                        const uint32_t cnt = staged_count<FW>(smem_addr(sp), rx[k] & 0xFFFFu);
                                         dst[idx] = make_uint2(rx[k] >> 16, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
                                     }
                                 }
@@ -608,7 +649,7 @@ __global__ void __launch_bounds__(640, 1)
                                     const bool alive = xb <= x && x < xd;
                                     const unsigned bm = __ballot_sync(kFull, alive);
                                     if (alive) {
-                                        const uint32_t cnt = *reinterpret_cast<const uint16_t*>(sp + (rx[k] & 0xFFFFu) * 2u);
+                                        const uint32_t cnt = staged_count<FW>(smem_addr(sp), rx[k] & 0xFFFFu);
                                         dst[at + (uint32_t)__popc(bm & lanemask_lt())] =
                                             make_uint2(rx[k] >> 16, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
                                     }

@@ -37,7 +37,8 @@ struct Geo {
     uint32_t in_row_stride;        // input view: sample(n,p,c) = in[n*in_chunk_stride + p*in_row_stride + c]
     uint64_t in_chunk_stride;
     uint32_t TY, T;                // rows per emit CTA, tiles per chunk
-    uint32_t K, Bpad;              // 32-biome sets, bytes per count vector (= 32*K)
+    uint32_t K, Bpad;              // 32-biome sets, entries per count vector (= 32*K)
+    uint32_t FW;                   // bits per vertical window count: 8 while 2r+1 <= 255, else 16
     uint32_t R;                    // ring columns = span + 16 * stages
     uint32_t stages;               // batches the emit producers may run ahead of the consumers (2..6)
     uint32_t producers;            // producer warps of the emit kernel (1..4)
@@ -225,20 +226,33 @@ __device__ __noinline__ void vscan_flush(const uint32_t* stg, uint32_t* cv_blk, 
     for (uint32_t col = 0u; col < ncols; col++) dst[(size_t)col * cv_pitch] = stg[lane * 33u + col];
     __syncwarp();
 }
-// a tile's base vector: the window counts (<= 2r+1 <= 255) as bytes, by compact id
+// a tile's base vector: the window counts (<= 2r+1) by compact id, as bytes (fw = 8) or 16-bit words (fw = 16)
 template <int K>
-__device__ __noinline__ void vscan_dump(const uint32_t* st, uint8_t* dst8) {
+__device__ __noinline__ void vscan_dump(const uint32_t* st, uint8_t* dst8, uint32_t fw) {
     uint4* dst = reinterpret_cast<uint4*>(dst8);
+    if (fw == 8u) {
 #pragma unroll 2
-    for (int q = 0; q < 2 * K; q++) {
-        uint32_t v[4];
+        for (int q = 0; q < 2 * K; q++) {
+            uint32_t v[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const uint32_t* src = st + (size_t)(16 * q + 4 * e) * kVscanThreads;
-            v[e] = (src[0] & 0xFFu) | ((src[kVscanThreads] & 0xFFu) << 8) | ((src[2 * kVscanThreads] & 0xFFu) << 16) |
-                   (src[3 * kVscanThreads] << 24);
+            for (int e = 0; e < 4; e++) {
+                const uint32_t* src = st + (size_t)(16 * q + 4 * e) * kVscanThreads;
+                v[e] = (src[0] & 0xFFu) | ((src[kVscanThreads] & 0xFFu) << 8) | ((src[2 * kVscanThreads] & 0xFFu) << 16) |
+                       (src[3 * kVscanThreads] << 24);
+            }
+            dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
         }
-        dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll 2
+        for (int q = 0; q < 4 * K; q++) {
+            uint32_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t* src = st + (size_t)(8 * q + 2 * e) * kVscanThreads;
+                v[e] = (src[0] & 0xFFFFu) | (src[kVscanThreads] << 16);
+            }
+            dst[q] = make_uint4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
@@ -293,7 +307,8 @@ struct VscanState {
     __device__ __forceinline__ void flush(uint32_t line0) const { vscan_flush(stg, cv_blk, cv_pitch, ncols, line0, lane); }
     __device__ __forceinline__ void push(uint32_t idx, uint32_t value) const { stg[(idx & 31u) * 33u + lane] = value; }
 
-    __device__ __forceinline__ void dump(uint8_t* dst8) const { vscan_dump<K>(st, dst8); }
+    uint32_t fw;
+    __device__ __forceinline__ void dump(uint8_t* dst8) const { vscan_dump<K>(st, dst8, fw); }
 };
 
 template <int K, bool ALIGNED>   // ALIGNED: rows per tile (TY) is a multiple of 8
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     vs.ncols = min((uint32_t)T, g.PW - blockIdx.x * T);
     vs.lanebit = valid ? 1u << lane : 0u;
     vs.lane = lane;
+    vs.fw = g.FW;
 #pragma unroll 8
     for (int i = 0; i < Bpad; i++) vs.st[i * T] = 0u;
 #pragma unroll
@@ -327,8 +343,9 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     const uint32_t nblk = gridDim.x;
     uint32_t* mout = tmask + ((size_t)n * g.H * nblk + blockIdx.x) * Bpad;   // row y
     const size_t mstep = (size_t)nblk * Bpad;
-    uint8_t* bout = base + ((size_t)n * g.T * g.PW + c) * Bpad;    // tile 0
-    const size_t bstep = (size_t)g.PW * Bpad;
+    const size_t vbytes = (size_t)Bpad * g.FW / 8u;               // bytes of one base vector
+    uint8_t* bout = base + ((size_t)n * g.T * g.PW + c) * vbytes;  // tile 0
+    const size_t bstep = (size_t)g.PW * vbytes;
     const uint32_t two_r = 2u * g.r;
 
     // ---- rows 0 .. 2r: the first window fills up, nothing leaves ----

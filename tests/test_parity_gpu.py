@@ -115,25 +115,39 @@ def test_medium(shf, filt, oracle_mod, w, h, r, biomes, kind):
 
 
 @pytest.mark.parametrize("w,h,r,biomes,kind", [
-    (130, 96, 128, 12, "blocky"),    # 2r+1 = 257: window counts no longer fit 8 bits
+    (130, 96, 128, 12, "blocky"),    # 2r+1 = 257: vertical window counts no longer fit 8 bits (16-bit ring)
     (192, 192, 162, 5, "iid"),       # the reference benchmark's largest radius (STPTestHistogram.cpp:266-279)
-    (64, 48, 8, 1000, "iid"),        # more than 256 distinct values in one neighbourhood
-    (130, 96, 128, 1024, "iid"),     # BASELINE.json C5 corner: radius 128 x 1024 biomes
+    (64, 48, 8, 1000, "iid"),        # more than 256 distinct values in one neighbourhood: wide path
+    (130, 96, 128, 1024, "iid"),     # BASELINE.json C5 corner: radius 128 x 1024 biomes: wide path
     (96, 64, 64, 1024, "blocky"),
     (40, 40, 20, 5000, "iid"),
     (140, 30, 130, 300, "stripes"),
     (36, 150, 128, 400, "hstripes"),
     (64, 64, 32, 700, "rare"),
+    (140, 100, 128, 40, "iid"),      # 16-bit ring, K = 2
+    (150, 110, 200, 100, "iid"),     # 16-bit ring, K = 4
+    (120, 90, 254, 100, "blocky"),   # 2r+1 = 509, the largest window of the 16-bit ring, K = 4
+    (120, 90, 254, 200, "blocky"),   # ... with K = 8 one row's ring (557 columns x 512 B) exceeds shared memory: wide path
+    (100, 80, 254, 3, "iid"),        # counts near (2r+1)^2 = 259 081 need the 32-bit horizontal sums
+    (100, 80, 256, 3, "blocky"),     # 2r+1 = 513: wide path
+    (257, 64, 128, 1, "iid"),        # one value: every window count is exactly 257 and 66 049
 ])
-def test_wide_path(shf, filt, oracle_mod, w, h, r, biomes, kind):
-    """Shapes outside the register-list march (radius above 126 or more than 256 distinct values): shf_generic.cuh."""
+def test_large_radius_and_wide_path(shf, filt, oracle_mod, w, h, r, biomes, kind):
+    """Shapes outside the 8-bit ring: radius 128..254 (16-bit vertical counts, 32-bit window sums) and the wide path
+    (shf_generic.cuh: radius above 254 or more than 256 distinct values)."""
     rng = np.random.default_rng(w * 7919 + h * 31 + r)
     nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
     m = random_map(rng, w, h, biomes, kind, nn)
     buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
     got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
-    assert_same(got, oracle_mod.run_port(m, (w, h), nn, r), f"wide {w}x{h} r={r} B={biomes} {kind}")
-    assert buf.lastPlan()["k_sets"] == 0  # the wide path ran
+    assert_same(got, oracle_mod.run_port(m, (w, h), nn, r), f"{w}x{h} r={r} B={biomes} {kind}")
+    sx, sy = w * (nn[0] // 2), h * (nn[1] // 2)
+    distinct = len(np.unique(m[sy - r:sy + h + r, sx - r:sx + w + r]))
+    plan = buf.lastPlan()
+    if distinct > 256 or 2 * r + 1 > 511:
+        assert plan["k_sets"] == 0   # the wide path ran
+    elif distinct <= 128:
+        assert plan["k_sets"] > 0    # the event-list path ran (129..256 values: only while one row's ring fits)
     buf.close()
 
 

@@ -189,7 +189,7 @@ int dispatch_events(int K, shf_buffer* b, const Geo& g, cudaStream_t s) {
     return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
 }
 
-// phase 0: vertical scan + bins per row; phase 1: the emitting march
+// phase 0: vertical scan + event lists (bins per row); phase 1: emit
 template <int K>
 int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
@@ -428,7 +428,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     bool generic = bmax > 256u || g.span > 511u;
     if (!generic) {
         g.Bpad = 32u * K;
-        // march kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
+        // emit kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
         // `ppb` passes; with `np` producer warps ceil(np / ppb) batches are in production at once, and the ring must
         // hold one more batch than that besides the 2r+1 columns the consumers still read.
         const uint32_t ppb = (uint32_t)K * g.FW / 8u;
@@ -481,7 +481,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     st = size_output(b, g, h_totals, s, true);
     if (st != SHF_OK) return st;
 
-    // ---- emitting march ----
+    // ---- emit ----
     SHF_CUDA(b->mark(5, s));
     st = dispatch_chain(K, b, g, s, 1);
     if (st != SHF_OK) return st;

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// emit: producers as in march_kernel (vertical window counts into a shared-memory ring), consumers = one warp per row
+// emit: producer warps (vertical window counts into a shared-memory ring), consumers = one warp per row
 // ------------------------------------------------------------------------------------------------------------------
 // FW = bits per vertical window count in the ring: 8 while 2r+1 <= 255, else 16 (2r+1 <= 511; the horizontal window
 // counts then need 32 bits: (2r+1)^2 exceeds 65535 from r = 128 on).

@@ -1,5 +1,5 @@
 // shf_generic.cuh -- the wide path of the single histogram filter: any radius, up to kGenericMaxBiomes distinct sample
-// values per neighbourhood. Used when the register-list march of shf_kernels.cuh does not cover the shape (2r+1 > 255,
+// values per neighbourhood. Used when the event-list path of shf_events.cuh does not cover the shape (2r+1 > 511,
 // more than 256 distinct values, or a ring that does not fit shared memory). Same semantics, same outputs; it trades
 // the shared-memory ring of vertical window counts for re-counting the entering and leaving columns cell by cell
 // (O(r) work per pixel instead of O(bins)), which needs no storage proportional to radius x biomes.

@@ -9,14 +9,19 @@
 // Layout of the computation on the GPU (all coordinates halo-relative: column c in [0, W+2r), row p in [0, H+2r)):
 //   presence/dictionary : distinct sample values of a chunk -> dense ids 0..B-1 ("compact ids"), cmap = remapped map
 //   vscan               : one thread per column walks down the rows and writes
-//                           vstart(c,p)  = first row of the vertical presence chain the sample at (c,p) belongs to
-//                                          (the reference's vertical accumulator keeps a bin alive across gaps <= 2r+1),
-//                           base(c,t)    = per-biome counts of the vertical window of the first row of row-tile t
-//   march<count>        : per row, slide the window left to right keeping the ordered bin list in registers, only
-//                         counting bins -> bins per row -> exclusive scan = first-bin index of every row
-//   march<emit>         : the same march, now writing HistogramStartOffset and the normalised bins in place
-// The march kernel is the hot one: a CTA owns TY consecutive rows (one warp per row); the vertical window counts of
-// the columns it walks over live in a shared-memory ring of (2r+1+NB) columns x TY rows x B bytes.
+//                           cvt(c,p)     = (compact id, first row of the vertical presence chain the sample at (c,p)
+//                                          belongs to; the reference's vertical accumulator keeps a bin alive across
+//                                          gaps <= 2r+1), column-major,
+//                           tmask(y,blk) = per value the 32 column bits "occurs in the vertical window of row y",
+//                           base(c,t)    = per-value counts of the vertical window of the first row of row-tile t
+//   events (shf_events.cuh) : per output row the presence chains of every value along the columns = the life spans of
+//                         the reference accumulator's bins, sorted by birth; their pixel spans total the bins per row
+//   rowscan             : exclusive scan of the bins per row = first-bin index of every row, chunk totals
+//   emit (shf_events.cuh)   : a CTA owns TY consecutive rows (one consumer warp per row); producer warps rebuild the
+//                         vertical window counts of the columns into a shared-memory ring of (2r+1 + 16*stages)
+//                         columns x TY rows x 32K counts; consumers slide them horizontally and write every pixel's
+//                         bins (the alive chains in list order) and HistogramStartOffset in place
+// Shapes this does not cover (2r+1 > 511, more than 256 distinct values) take shf_generic.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

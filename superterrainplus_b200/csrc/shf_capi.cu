@@ -439,11 +439,23 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             g.R = g.span + shf::kMarchNB * g.stages;
         };
         auto smem_of = [&](uint32_t t) { return emit_smem(t, g.R, K, (int)g.FW); };
-        plan(4u, 2u);
-        if (smem_of(ty) > f->smem_optin) plan(4u, 1u);
-        if (smem_of(ty) > f->smem_optin) plan(2u, 1u);
-        if (smem_of(ty) > f->smem_optin) plan(1u, 1u);
-        while (ty > 1u && smem_of(ty) > f->smem_optin) ty--;
+        // Keep the four producer warps and give up rows per CTA first (a starved consumer warp costs more than a smaller
+        // tile): of the two ring depths with four producers take the one that fits more rows; fewer producers only
+        // when not even two rows fit with four.
+        const uint32_t ty_max = ty;
+        auto rows_that_fit = [&](uint32_t np, uint32_t extra) {
+            plan(np, extra);
+            uint32_t t = ty_max;
+            while (t > 1u && smem_of(t) > f->smem_optin) t--;
+            return smem_of(t) <= f->smem_optin ? t : 0u;
+        };
+        const uint32_t deep = rows_that_fit(4u, 2u), shallow = rows_that_fit(4u, 1u);
+        if (std::max(deep, shallow) >= std::min(2u, ty_max)) {
+            ty = std::max(deep, shallow);
+            plan(4u, deep >= shallow ? 2u : 1u);
+        } else if ((ty = rows_that_fit(2u, 1u)) == 0u) {
+            ty = std::max(1u, rows_that_fit(1u, 1u));   // (does not fit either: the check below sends it to the wide path)
+        }
         // small calls: 8 rows per CTA when 16 would leave more than half of the SMs idle (a single 512x512 chunk has 32
         // tiles of 16 rows: emit 0.054 -> 0.046 ms; a 2048x2048 chunk with its 128 tiles is better off with 16)
         // (8, not fewer: vscan dumps a base vector per tile and its fast variant wants multiples of 8)

@@ -30,13 +30,19 @@ for case in range(n_cases):
     n = int(rng.choice([1, 1, 2, 3]))
     maps = [random_map(rng, w, h, biomes, kind, nn) for _ in range(n)]
     info = shf.STPNearestNeighbourInformation((w, h), nn, (w * nn[0], h * nn[1]))
-    hist = filt.runBatch(maps, info, buf, r)
-    base = buf.chunkBase()
-    per = w * h + 1
-    for i, m in enumerate(maps):
-        got = (hist.Bin["Item"][base[i]:base[i + 1]].copy(), hist.Bin["Weight"][base[i]:base[i + 1]].copy(),
-               hist.HistogramStartOffset[i * per:(i + 1) * per].copy())
-        assert_same(got, oracle.run_port(m, (w, h), nn, r), f"case {case}: {w}x{h} r={r} B={biomes} {kind} nn={nn} chunk {i}/{n}")
+    want = [oracle.run_port(m, (w, h), nn, r) for m in maps]
+    # the first call on a shape takes the checked path, a repeated one runs ahead with the previous plan; a third call
+    # with other maps of the same shape (possibly more distinct values or more bins than the buffers hold) must notice
+    for rep, batch in enumerate((maps, maps, [random_map(rng, w, h, int(rng.choice([biomes, 2 * biomes + 3])), kind, nn)
+                                              for _ in range(n)])):
+        hist = filt.runBatch(batch, info, buf, r)
+        base = buf.chunkBase()
+        per = w * h + 1
+        for i, m in enumerate(batch):
+            got = (hist.Bin["Item"][base[i]:base[i + 1]].copy(), hist.Bin["Weight"][base[i]:base[i + 1]].copy(),
+                   hist.HistogramStartOffset[i * per:(i + 1) * per].copy())
+            ref = want[i] if rep < 2 else oracle.run_port(m, (w, h), nn, r)
+            assert_same(got, ref, f"case {case} call {rep}: {w}x{h} r={r} B={biomes} {kind} nn={nn} chunk {i}/{n}")
     p = buf.lastPlan()
     key = (p["k_sets"], 16 if 2 * r + 1 > 255 and p["k_sets"] else 8 if p["k_sets"] else 0)
     plans[key] = plans.get(key, 0) + 1

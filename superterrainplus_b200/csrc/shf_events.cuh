@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(640, 1)
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
     const uint32_t y0 = tile * TY;
     const uint32_t NP = g.producers;
+    // a call that runs ahead of the host's size checks must stay inside the buffers it was given (the host then sees the
+    // totals, grows the buffers and runs the call again)
+    if (chunkbase[n_chunk + 1u] > g.bins_cap) return;
     const uint32_t n_batches = (PW + NB - 1u) / NB;
 
     uint8_t* cring = smem;
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(640, 1)
     uint2* act = act_all + (size_t)warp * ACAP;
     const uint2 ri = row_active ? rowinfo[(size_t)n_chunk * g.H + y] : make_uint2(0u, 0u);
     const uint2* ev = pool + ri.x;
-    const uint32_t E = ri.y;
+    const uint32_t E = (unsigned long long)ri.x + ri.y <= g.pool_cap ? ri.y : 0u;
     uint32_t off = row_active ? rowbase[(size_t)n_chunk * g.H + y] : 0u;  // offset of the next pixel's first bin
     uint2* dst = bins + (row_active ? (size_t)chunkbase[n_chunk] + off : (size_t)0);
     uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;

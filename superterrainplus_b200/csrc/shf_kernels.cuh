@@ -50,6 +50,7 @@ struct Geo {
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
+    unsigned long long bins_cap, pool_cap;  // capacities of the bin buffer / event pool (guards of a speculative call)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -162,7 +163,9 @@ __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint3
         pf[i] = prefix[(size_t)n * kDictWords + i];
     }
     __syncthreads();
-    auto rank = [&](uint32_t s) { return pf[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31u)) - 1u)); };
+    // (the clamp only bites when a repeated call runs with the previous call's plan and this map has more distinct
+    // values than that plan holds: the result is then discarded and recomputed, but no kernel may index out of range)
+    auto rank = [&](uint32_t s) { return min(pf[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31u)) - 1u)), dict_stride - 1u); };
     const uint16_t* src = in + (size_t)n * g.in_chunk_stride;
     const uint32_t rows_per = (g.PH + gridDim.x - 1u) / gridDim.x;
     const uint32_t p0 = blockIdx.x * rows_per, p1 = min(g.PH, p0 + rows_per);
@@ -524,6 +527,34 @@ __global__ void rowscan_kernel(Geo g, const uint32_t* __restrict__ rowtotal, uin
         chunktotal[n] = carry;
         hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)carry;
     }
+}
+
+// first-bin index of every chunk on the device (exclusive scan of the chunk totals; chunkbase[n_chunks] = all bins):
+// lets a repeated call launch its emit kernel without waiting for the host to see the totals
+__global__ void chunkbase_kernel(uint32_t n_chunks, const unsigned long long* __restrict__ chunktotal,
+                                 unsigned long long* __restrict__ chunkbase) {
+    __shared__ unsigned long long part[1024];
+    __shared__ unsigned long long carry;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) carry = 0ull;
+    __syncthreads();
+    for (uint32_t i0 = 0u; i0 < n_chunks; i0 += blockDim.x) {
+        const uint32_t i = i0 + t;
+        const unsigned long long v = i < n_chunks ? chunktotal[i] : 0ull;
+        part[t] = v;
+        __syncthreads();
+        for (uint32_t off = 1u; off < blockDim.x; off <<= 1) {
+            const unsigned long long add = (t >= off) ? part[t - off] : 0ull;
+            __syncthreads();
+            part[t] += add;
+            __syncthreads();
+        }
+        if (i < n_chunks) chunkbase[i] = carry + part[t] - v;
+        __syncthreads();
+        if (t == blockDim.x - 1) carry += part[t];
+        __syncthreads();
+    }
+    if (t == 0) chunkbase[n_chunks] = carry;
 }
 
 }  // namespace shf

@@ -2,7 +2,7 @@
 # tests + fuzz + single-chunk lines with and without the run-ahead path
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu -x --timeout 900 2>&1 | tail -4
-python scripts/gpu_fuzz.py 300 11 | tail -1
+python tests/fuzz_gpu.py 300 11 | tail -1
 for spec in 1 0; do
 for v in "--workload C1 --dist uniform" "--workload C2 --dist uniform" "--workload C2 --dist blocky" "--workload C4 --dist blocky" "--workload C3 --dist uniform" "--workload C3 --dist blocky"; do
   if [ $spec = 0 ]; then export SHF_NO_SPECULATION=1; else unset SHF_NO_SPECULATION; fi

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Randomised differential test on a GPU: random shapes, radii (8-bit ring, 16-bit ring, wide path), biome counts
-(K = 1..8 and beyond), map kinds and batch sizes against the CPU oracle, bit for bit. usage: gpu_fuzz.py [cases] [seed]"""
-import sys, time
-sys.path.insert(0, ".")
-sys.path.insert(0, "tests")
+(K = 1..8 and beyond), map kinds and batch sizes against the CPU oracle, bit for bit. usage: python tests/fuzz_gpu.py [cases] [seed]
+(test infrastructure: run by tests/test_fuzz_gpu.py; the oracle is the checker)"""
+import os, sys, time
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+sys.path.insert(0, _HERE)
 import numpy as np
 import oracle
 import superterrainplus_b200 as shf

@@ -898,7 +898,7 @@ int shf_heightfield_create(shf_heightfield** out, shf_filter* f, const shf_biome
     *out = nullptr;
     if (n_table == 0u || gradient2d_size == 0u)
         return fail(SHF_ERR_INVALID_ARGUMENT, "n_table > 0 && gradient2d_size > 0", "empty table");
-    const size_t smem = 512 + (size_t)gradient2d_size * 8 + (size_t)n_table * sizeof(shf_biome_property);
+    const size_t smem = 1024 + (size_t)gradient2d_size * 8 + (size_t)n_table * sizeof(shf_biome_property);
     if (smem > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "tables fit shared memory", "biome / gradient tables too large for one CTA");
     SHF_CUDA(cudaSetDevice(f->device));
@@ -955,7 +955,7 @@ int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk,
     g.grad_size = h->grad_size;
     g.half_x = (float)g.W / 2.0f;
     g.half_y = (float)g.H / 2.0f;
-    const size_t smem = 512 + (size_t)h->grad_size * 8 + (size_t)h->n_table * sizeof(shf_biome_property);
+    const size_t smem = 1024 + (size_t)h->grad_size * 8 + (size_t)h->n_table * sizeof(shf_biome_property);
     SHF_CUDA(cudaFuncSetAttribute(shf::heightfield_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t npx = g.W * g.H;
     const uint32_t gx = std::max(1u, std::min((npx + 255u) / 256u, 148u * 8u));

@@ -29,8 +29,9 @@ __device__ __forceinline__ int hf_floori(float x) {  // STPSimplexNoise.cu:14-16
 }
 
 // STPSimplexNoise.cu:18-82 with explicit roundings
-__device__ __forceinline__ float hf_simplex2d(const unsigned char* __restrict__ perm, const float2* __restrict__ grad,
-                                              uint32_t grad_size, float x, float y) {
+// `pgrad[i]` = perm[i] % grad_size, tabulated once per CTA (the reference takes the modulo at every corner)
+__device__ __forceinline__ float hf_simplex2d(const unsigned char* __restrict__ perm, const unsigned char* __restrict__ pgrad,
+                                              const float2* __restrict__ grad, float x, float y) {
     const float F2 = 0.3660254038f, G2 = 0.2113248654f, H2 = -1.0f + 2.0f * 0.2113248654f;
     const float s = __fmul_rn(__fadd_rn(x, y), F2);
     const int i = hf_floori(__fadd_rn(x, s)), j = hf_floori(__fadd_rn(y, s));
@@ -46,9 +47,9 @@ __device__ __forceinline__ float hf_simplex2d(const unsigned char* __restrict__ 
     dy[2] = __fadd_rn(dy[0], H2);
     const uint32_t ii = (uint32_t)i & 255u, jj = (uint32_t)j & 255u;
     uint32_t gi[3];
-    gi[0] = perm[ii + perm[jj]] % grad_size;
-    gi[1] = perm[ii + i1 + perm[jj + j1]] % grad_size;
-    gi[2] = perm[ii + 1u + perm[jj + 1u]] % grad_size;
+    gi[0] = pgrad[ii + perm[jj]];
+    gi[1] = pgrad[ii + i1 + perm[jj + j1]];
+    gi[2] = pgrad[ii + 1u + perm[jj + 1u]];
     float corner[3];
 #pragma unroll
     for (int v = 0; v < 3; v++) {
@@ -66,14 +67,15 @@ __device__ __forceinline__ float hf_simplex2d(const unsigned char* __restrict__ 
 }
 
 // STPSimplexNoise.cu:84-109 (initial amplitude and frequency 1, STPSimplexNoise.cuh:46-51)
-__device__ __forceinline__ float hf_fractal(const unsigned char* __restrict__ perm, const float2* __restrict__ grad,
-                                            uint32_t grad_size, float x, float y, const shf_biome_property& p, float off_x,
-                                            float off_y, float half_x, float half_y) {
+__device__ __forceinline__ float hf_fractal(const unsigned char* __restrict__ perm, const unsigned char* __restrict__ pgrad,
+                                            const float2* __restrict__ grad, float bx, float by, const shf_biome_property& p) {
     float fractal = 0.0f, amplitude = 1.0f, frequency = 1.0f, range = 0.0f;
-    const float bx = __fadd_rn(__fsub_rn(x, half_x), off_x), by = __fadd_rn(__fsub_rn(y, half_y), off_y);
+    // (x / scale) * frequency per octave in the reference: the quotient does not depend on the octave, so the two IEEE
+    // divisions are done once per bin -- same operands, same roundings
+    const float qx = __fdiv_rn(bx, p.scale), qy = __fdiv_rn(by, p.scale);
     for (uint32_t o = 0u; o < p.octave; o++) {
-        const float sx = __fmul_rn(__fdiv_rn(bx, p.scale), frequency), sy = __fmul_rn(__fdiv_rn(by, p.scale), frequency);
-        fractal = __fmaf_rn(hf_simplex2d(perm, grad, grad_size, sx, sy), amplitude, fractal);
+        const float sx = __fmul_rn(qx, frequency), sy = __fmul_rn(qy, frequency);
+        fractal = __fmaf_rn(hf_simplex2d(perm, pgrad, grad, sx, sy), amplitude, fractal);
         range = __fadd_rn(range, amplitude);
         amplitude = __fmul_rn(amplitude, p.persistence);
         frequency = __fmul_rn(frequency, p.lacunarity);
@@ -82,7 +84,7 @@ __device__ __forceinline__ float hf_fractal(const unsigned char* __restrict__ pe
 }
 
 // One thread per pixel; the lookup tables sit in shared memory. blockIdx.y = chunk of the batch.
-// smem: perm[512] | grad[grad_size] float2 | table[n_table] shf_biome_property
+// smem: perm[512] | pgrad[512] | grad[grad_size] float2 | table[n_table] shf_biome_property
 __global__ void __launch_bounds__(256) heightfield_kernel(HeightGeo g, const uint2* __restrict__ bins,
                                                           const uint32_t* __restrict__ hso,
                                                           const uint64_t* __restrict__ chunkbase, uint32_t first_chunk,
@@ -92,9 +94,14 @@ __global__ void __launch_bounds__(256) heightfield_kernel(HeightGeo g, const uin
                                                           const float2* __restrict__ offsets, float* __restrict__ height) {
     extern __shared__ __align__(16) uint8_t smem[];
     unsigned char* perm = smem;
-    float2* grad = reinterpret_cast<float2*>(smem + 512);
-    shf_biome_property* tab = reinterpret_cast<shf_biome_property*>(smem + 512 + (size_t)g.grad_size * 8);
-    for (uint32_t i = threadIdx.x; i < 512u; i += blockDim.x) perm[i] = perm_g[i];
+    unsigned char* pgrad = smem + 512;
+    float2* grad = reinterpret_cast<float2*>(smem + 1024);
+    shf_biome_property* tab = reinterpret_cast<shf_biome_property*>(smem + 1024 + (size_t)g.grad_size * 8);
+    for (uint32_t i = threadIdx.x; i < 512u; i += blockDim.x) {
+        const unsigned char pv = perm_g[i];
+        perm[i] = pv;
+        pgrad[i] = (unsigned char)((uint32_t)pv % g.grad_size);
+    }
     for (uint32_t i = threadIdx.x; i < g.grad_size; i += blockDim.x) grad[i] = make_float2(grad_g[2u * i], grad_g[2u * i + 1u]);
     for (uint32_t i = threadIdx.x; i < g.n_table; i += blockDim.x) tab[i] = table[i];
     __syncthreads();
@@ -106,13 +113,15 @@ __global__ void __launch_bounds__(256) heightfield_kernel(HeightGeo g, const uin
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += gridDim.x * blockDim.x) {
         const uint32_t begin = ho[p], end = ho[p + 1u];  // STPSingleHistogramWrapper.inl:9-12
         const float x = (float)(p % g.W), y = (float)(p / g.W);
+        // the sample position before scaling is the same for every bin of the pixel (STPSimplexNoise.cu:93-96)
+        const float bx = __fadd_rn(__fsub_rn(x, g.half_x), off.x), by = __fadd_rn(__fsub_rn(y, g.half_y), off.y);
         float h = 0.0f;
         for (uint32_t b = begin; b < end; b++) {
             const uint2 bin = cb[b];
             const uint32_t item = bin.x & 0xFFFFu;
             if (item >= g.n_table) continue;  // the reference indexes its table unchecked; contribute nothing instead
             const shf_biome_property pr = tab[item];
-            const float noise = hf_fractal(perm, grad, g.grad_size, x, y, pr, off.x, off.y, g.half_x, g.half_y);
+            const float noise = hf_fractal(perm, pgrad, grad, bx, by, pr);
             h = __fmaf_rn(__uint_as_float(bin.y), __fmaf_rn(noise, pr.variation, pr.depth), h);
         }
         height[(size_t)blockIdx.y * npx + p] = h;

@@ -53,15 +53,13 @@ __device__ __forceinline__ float hf_simplex2d(const unsigned char* __restrict__ 
     float corner[3];
 #pragma unroll
     for (int v = 0; v < 3; v++) {
-        float w = __fsub_rn(__fsub_rn(0.5f, __fmul_rn(dx[v], dx[v])), __fmul_rn(dy[v], dy[v]));
-        if (w <= 0.0f) {
-            corner[v] = 0.0f;
-        } else {
-            w = __fmul_rn(w, w);
-            const float2 gr = grad[gi[v]];
-            const float dot = __fmaf_rn(gr.x, dx[v], __fmul_rn(gr.y, dy[v]));
-            corner[v] = __fmul_rn(__fmul_rn(w, w), dot);
-        }
+        // the reference returns 0 for w <= 0; clamping w to 0 gives (+-)0 * dot = (+-)0 instead, and a signed zero
+        // changes neither the corner sum nor the fma into the octave sum -- no branch, same bits
+        float w = fmaxf(__fsub_rn(__fsub_rn(0.5f, __fmul_rn(dx[v], dx[v])), __fmul_rn(dy[v], dy[v])), 0.0f);
+        w = __fmul_rn(w, w);
+        const float2 gr = grad[gi[v]];
+        const float dot = __fmaf_rn(gr.x, dx[v], __fmul_rn(gr.y, dy[v]));
+        corner[v] = __fmul_rn(__fmul_rn(w, w), dot);
     }
     return __fmul_rn(70.0f, __fadd_rn(__fadd_rn(corner[0], corner[1]), corner[2]));
 }

@@ -107,7 +107,7 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
-        bins, hso, gstate, evpool, rowinfo, cvt;
+        bins, hso, gstate, evpool, rowinfo, cvt, vexit;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
     uint32_t n_chunks = 0, last_w = 0, last_h = 0;
@@ -144,7 +144,7 @@ struct shf_buffer {
         last_valid = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
                        &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
-                       &evpool, &rowinfo, &cvt};
+                       &evpool, &rowinfo, &cvt, &vexit};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -198,16 +198,27 @@ int dispatch_events(int K, shf_buffer* b, const Geo& g, cudaStream_t s) {
 template <int K>
 int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
-        const dim3 vgrid((g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads, g.n_chunks);
+        const uint32_t nblk = (g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads;
+        const dim3 vgrid(nblk, g.n_chunks, g.vseg);
         const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K + 32 * 33 * 4;
+        if (g.vseg > 1u) SHF_CUDA(b->vexit.ensure((size_t)g.n_chunks * (g.vseg - 1u) * nblk * 32 * K * 32 * 4));
         if (g.TY % 8u == 0u) {
             SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
             shf::vscan_kernel<K, true><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
-                                                                               b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
+                                                                               b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
+                                                                               b->vexit.as<uint32_t>());
         } else {
             SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
             shf::vscan_kernel<K, false><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
-                                                                                b->base.as<uint8_t>(), b->colmask.as<uint32_t>());
+                                                                                b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
+                                                                                b->vexit.as<uint32_t>());
+        }
+        if (g.vseg > 1u) {
+            // chain starts the row segments could not know
+            const uint32_t rows = g.H - (1u + g.vseg_rows);
+            shf::vpatch_kernel<<<dim3((rows + 255u) / 256u, g.PW, g.n_chunks), 256, 0, s>>>(g, nblk, b->cvt.as<uint32_t>(),
+                                                                                             b->vexit.as<uint32_t>());
+            tls_launches++;
         }
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
@@ -553,6 +564,23 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             g.TY = ty;
             g.T = (H + ty - 1u) / ty;
             b->plan_smem = (uint32_t)smem_of(ty);
+        }
+        // vscan walks every column top to bottom, one warp per 32 columns: a small call (a single 1024x1024 chunk has 36
+        // such warps) is split into up to four row segments per block, each replaying the 2r+1 rows above its first
+        g.vseg = 1u;
+        g.vseg_rows = 0u;
+        const uint64_t vwarps = (uint64_t)n_chunks * ((g.PW + 31u) / 32u);
+        if (!generic && vwarps < 2ull * (uint64_t)f->sm_count && !getenv("SHF_NO_VSEG")) {
+            uint32_t S = 4u;
+            while (S > 1u) {
+                const uint32_t L = (((H - 1u) + S - 1u) / S + 31u) & ~31u;   // output rows per segment
+                if (L >= std::max(64u, g.span / 2u) && 1u + (S - 1u) * L < H && vwarps * S <= 4ull * (uint64_t)f->sm_count) {
+                    g.vseg = S;
+                    g.vseg_rows = L;
+                    break;
+                }
+                S--;
+            }
         }
     }
     b->plan_k = generic ? 0u : (uint32_t)K;

@@ -33,6 +33,7 @@ constexpr int kDictWords = 2048;      // 65536 possible sample values / 32
 constexpr int kVscanThreads = 32;     // columns per CTA in vscan (one warp: small CTAs spread single-chunk calls over the SMs)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kNoRow = 0xFFFFu;
+constexpr uint32_t kTentative = 0xFFFFu;  // chain start not known inside a vscan row segment (rows are < 65535)
 
 struct Geo {
     uint32_t W, H, r, span;        // chunk map size, radius, 2r+1
@@ -49,6 +50,7 @@ struct Geo {
     uint32_t producers;            // producer warps of the emit kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
+    uint32_t vseg, vseg_rows;      // vscan row segments per column block (1 = none) and output rows per segment (x32)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
     unsigned long long bins_cap, pool_cap;  // capacities of the bin buffer / event pool (guards of a speculative call)
 };
@@ -280,6 +282,15 @@ struct VscanState {
         if (born) atomicOr(&tm[s], lanebit);
         return w >> 16;
     }
+    // replay of a row segment's first window: counts only, every chain met here began somewhere above
+    __device__ __forceinline__ void enter_tentative(uint32_t s) {
+        uint32_t w = st[s * kVscanThreads];
+        if ((w & 0xFFFFu) == 0u) {
+            w = kTentative << 16;
+            atomicOr(&tm[s], lanebit);
+        }
+        st[s * kVscanThreads] = w + 1u;
+    }
     __device__ __forceinline__ void leave(uint32_t o) {
         const uint32_t w = st[o * kVscanThreads] - 1u;
         st[o * kVscanThreads] = w;
@@ -322,7 +333,7 @@ struct VscanState {
 template <int K, bool ALIGNED>   // ALIGNED: rows per tile (TY) is a multiple of 8
 __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint16_t* __restrict__ cmap,
                                                               uint32_t* __restrict__ cvt, uint8_t* __restrict__ base,
-                                                              uint32_t* __restrict__ tmask) {
+                                                              uint32_t* __restrict__ tmask, uint32_t* __restrict__ vexit) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int Bpad = 32 * K;
     constexpr int T = kVscanThreads;
@@ -356,54 +367,76 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     const size_t bstep = (size_t)g.PW * vbytes;
     const uint32_t two_r = 2u * g.r;
 
-    // ---- rows 0 .. 2r: the first window fills up, nothing leaves ----
-    uint32_t p = 0u;
-    for (; p + 8u <= two_r + 1u; p += 8u) {
-        uint32_t s_in[8];
+    // Row segments (blockIdx.z; small calls only, see vseg in the plan): segment k > 0 starts at output row
+    // Y = 1 + k * vseg_rows. It rebuilds the window state of row Y - 1 by replaying that window's 2r+1 rows -- the
+    // counts come out exact, the chain starts cannot (a chain may have begun anywhere above): they are marked
+    // kTentative, travel into cvt as such while the chain lasts, and vpatch_kernel replaces them by the start the
+    // segment above ended with (its exit state, written below).
+    const uint32_t seg = blockIdx.z, n_seg = g.vseg;
+    const uint32_t y_first = seg == 0u ? 0u : 1u + seg * g.vseg_rows;
+    const uint32_t y_end = seg + 1u < n_seg ? 1u + (seg + 1u) * g.vseg_rows : g.H;
+    uint32_t next_dump = g.TY;   // the next tile's first row
+    if (seg == 0u) {
+        // ---- rows 0 .. 2r: the first window fills up, nothing leaves ----
+        uint32_t p = 0u;
+        for (; p + 8u <= two_r + 1u; p += 8u) {
+            uint32_t s_in[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) s_in[j] = in[j * P];
+            for (int j = 0; j < 8; j++) s_in[j] = in[j * P];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            vs.push(ci, s_in[j] | (vs.enter(s_in[j], p + j) << 16));
-            if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+            for (int j = 0; j < 8; j++) {
+                vs.push(ci, s_in[j] | (vs.enter(s_in[j], p + j) << 16));
+                if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+            }
+            in += 8 * P;
         }
-        in += 8 * P;
+        for (; p <= two_r; p++) {
+            const uint32_t sv = *in;
+            vs.push(ci, sv | (vs.enter(sv, p) << 16));
+            if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+            in += P;
+        }
+        vs.store_mask(mout);
+        mout += mstep;
+        if (valid) vs.dump(bout);
+        bout += bstep;
+    } else {
+        // ---- replay of the window of output row y_first - 1: rows y_first - 1 .. y_first + 2r - 1 ----
+        in += (size_t)(y_first - 1u) * P;
+        for (uint32_t q = 0u; q <= two_r; q++) {
+            vs.enter_tentative(*in);
+            in += P;
+        }
+        ci = g.cv_pad + y_first + two_r;                       // a multiple of 32 by construction
+        mout += (size_t)y_first * mstep;
+        const uint32_t t0 = (y_first + g.TY - 1u) / g.TY;       // first tile starting inside this segment
+        bout += (size_t)t0 * bstep;
+        next_dump = t0 * g.TY;
     }
-    for (; p <= two_r; p++) {
-        const uint32_t sv = *in;
-        vs.push(ci, sv | (vs.enter(sv, p) << 16));
-        if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
-        in += P;
-    }
-    vs.store_mask(mout);
-    mout += mstep;
-    if (valid) vs.dump(bout);
-    bout += bstep;
 
     // ---- output rows 1 .. H-1: row y + 2r enters, row y - 1 leaves ----
-    const uint16_t* out = cmap + (size_t)n * g.PH * P + c;     // row y - 1 (leaving)
-    uint32_t y = 1u;
-    uint32_t next_dump = g.TY;   // the next tile's first row
+    uint32_t y = seg == 0u ? 1u : y_first;
+    const uint16_t* out = cmap + (size_t)n * g.PH * P + c + (size_t)(y - 1u) * P;     // row y - 1 (leaving)
     // groups of 8 rows; the samples of a group are loaded while the group before it is processed (one DRAM round trip
     // hidden per group). With TY a multiple of 8 a tile's first row is always the last row of a group (ALIGNED); other
     // plans check every row.
     {
         uint32_t n_in[8], n_out[8];
-        if (y + 8u <= g.H) {
+        if (y + 8u <= y_end) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 n_in[j] = in[j * P];
                 n_out[j] = out[j * P];
             }
         }
-        for (; y + 8u <= g.H; y += 8u) {
+        for (; y + 8u <= y_end; y += 8u) {
             uint32_t s_in[8], s_out[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 s_in[j] = n_in[j];
                 s_out[j] = n_out[j];
             }
-            if (y + 16u <= g.H) {
+            if (y + 16u <= y_end) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     n_in[j] = in[(8 + j) * P];
@@ -432,7 +465,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             }
         }
     }
-    for (; y < g.H; y++) {
+    for (; y < y_end; y++) {
         const uint32_t sv = *in;
         vs.push(ci, sv | (vs.step(sv, *out, two_r + y) << 16));
         if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
@@ -447,6 +480,31 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         }
     }
     if (ci & 31u) vs.flush(ci & ~31u);
+    // exit state for the segment below: (count, start) of every value in this column
+    if (seg + 1u < n_seg) {
+        uint32_t* ex = vexit + ((((size_t)n * (n_seg - 1u) + seg) * gridDim.x + blockIdx.x) * Bpad) * T + lane;
+#pragma unroll 8
+        for (int i = 0; i < Bpad; i++) ex[i * T] = vs.st[i * T];
+    }
+}
+
+// Chain starts a row segment could not know (kTentative): the chain was alive when the segment began, so its start is
+// the one the segment above ended with for that value -- or, if that one is tentative as well, the one above it.
+__global__ void vpatch_kernel(Geo g, uint32_t nblk, uint32_t* __restrict__ cvt, const uint32_t* __restrict__ vexit) {
+    const uint32_t n = blockIdx.z, c = blockIdx.y;
+    const uint32_t first = 1u + g.vseg_rows;                    // first output row of segment 1
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // cell = entering row of output row first + i
+    if (first + i >= g.H) return;
+    const uint32_t y = first + i;
+    const uint32_t seg = min((y - 1u) / g.vseg_rows, g.vseg - 1u);
+    uint32_t* cell = cvt + ((size_t)n * g.PW + c) * g.cv_pitch + g.cv_pad + y + 2u * g.r;
+    const uint32_t v = *cell;
+    if ((v >> 16) != kTentative) return;
+    const uint32_t id = v & 0xFFFFu, Bpad = g.Bpad;
+    uint32_t start = kTentative;
+    for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
+        start = vexit[((((size_t)n * (g.vseg - 1u) + k) * nblk + c / 32u) * Bpad + id) * 32u + (c & 31u)] >> 16;
+    *cell = id | (start << 16);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -566,12 +566,13 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             b->plan_smem = (uint32_t)smem_of(ty);
         }
         // vscan walks every column top to bottom, one warp per 32 columns: a small call (a single 1024x1024 chunk has 36
-        // such warps) is split into up to four row segments per block, each replaying the 2r+1 rows above its first
+        // such warps) is split into up to eight row segments per block, each replaying the 2r+1 rows above its first
         g.vseg = 1u;
         g.vseg_rows = 0u;
         const uint64_t vwarps = (uint64_t)n_chunks * ((g.PW + 31u) / 32u);
         if (!generic && vwarps < 2ull * (uint64_t)f->sm_count && !getenv("SHF_NO_VSEG")) {
-            uint32_t S = 4u;
+            uint32_t S = 8u;
+            if (const char* e = getenv("SHF_DEBUG_VSEG")) S = std::max(1u, (uint32_t)atoi(e));  // measurements only
             while (S > 1u) {
                 const uint32_t L = (((H - 1u) + S - 1u) / S + 31u) & ~31u;   // output rows per segment
                 if (L >= std::max(64u, g.span / 2u) && 1u + (S - 1u) * L < H && vwarps * S <= 4ull * (uint64_t)f->sm_count) {

@@ -212,6 +212,31 @@ def test_config5_radius_biome_sweep(shf, filt, oracle_mod, r, biomes, kind):
     buf.close()
 
 
+@pytest.mark.parametrize("w,h,r,biomes,kind,segments", [
+    (70, 300, 8, 6, "rare", 4), (70, 300, 8, 30, "hstripes", 8), (96, 260, 32, 12, "blocky", 3), (64, 200, 64, 5, "iid", 2),
+    (40, 520, 16, 70, "iid", 8), (130, 400, 100, 3, "blocky", 3), (50, 330, 130, 9, "hstripes", 2), (33, 700, 4, 2, "rare", 8),
+])
+def test_vscan_row_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segments, monkeypatch):
+    """Small calls split the vertical scan into row segments whose chain starts are resolved afterwards (vpatch_kernel):
+    chains that never break (hstripes), chains that break inside segments (rare / small radius), 16-bit ring, and the
+    same map with the segmentation switched off must all agree with the oracle."""
+    rng = np.random.default_rng(w * 131 + h * 7 + r)
+    nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
+    m = random_map(rng, w, h, biomes, kind, nn)
+    want = oracle_mod.run_port(m, (w, h), nn, r)
+    for setting in (str(segments), None, "off"):
+        if setting == "off":
+            monkeypatch.setenv("SHF_NO_VSEG", "1")
+        elif setting is None:
+            monkeypatch.delenv("SHF_DEBUG_VSEG", raising=False)
+        else:
+            monkeypatch.setenv("SHF_DEBUG_VSEG", setting)
+        buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+        got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+        assert_same(got, want, f"{w}x{h} r={r} B={biomes} {kind} segments={setting}")
+        buf.close()
+
+
 def split_neighbours(m, w, h, nn):
     """The nn.x * nn.y chunk maps of a merged map, in local-index order (STPChunk::calcLocalChunkCoordinate)."""
     return [np.ascontiguousarray(m[cy * h:(cy + 1) * h, cx * w:(cx + 1) * w]) for cy in range(nn[1]) for cx in range(nn[0])]

@@ -229,7 +229,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     Geo ge = g;
     ge.bins_cap = b->bins.cap / sizeof(shf_bin);
     ge.pool_cap = b->evpool.cap / 8;
-    const dim3 grid(g.T, g.n_chunks);
+    const dim3 grid(g.T, g.n_chunks, g.cseg);
     const uint32_t threads = (g.TY + g.producers) * 32;
     if (g.FW == 8u) {
         SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -564,6 +564,25 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
             g.TY = ty;
             g.T = (H + ty - 1u) / ty;
             b->plan_smem = (uint32_t)smem_of(ty);
+        }
+        // emit walks every row left to right, one consumer warp per row: a small call (a single 1024x1024 chunk has 128
+        // tiles of 8 rows) is split into column segments, each sliding over the 2r columns before its first pixel
+        g.cseg = 1u;
+        g.cseg_px = W;
+        if (!generic && !getenv("SHF_NO_CSEG")) {
+            const uint64_t ctas = (uint64_t)n_chunks * g.T;
+            uint32_t want = ctas < 2ull * (uint64_t)f->sm_count ? (uint32_t)((2ull * f->sm_count + ctas - 1u) / ctas) : 1u;
+            if (const char* e = getenv("SHF_DEBUG_CSEG")) want = std::max(1u, (uint32_t)atoi(e));  // measurements only
+            want = std::min(want, 8u);
+            while (want > 1u) {
+                const uint32_t px = ((W + want - 1u) / want + 15u) & ~15u;
+                if (px >= std::max(64u, 2u * r)) {
+                    g.cseg_px = px;
+                    g.cseg = (W + px - 1u) / px;
+                    break;
+                }
+                want--;
+            }
         }
         // vscan walks every column top to bottom, one warp per 32 columns: a small call (a single 1024x1024 chunk has 36
         // such warps) is split into up to eight row segments per block, each replaying the 2r+1 rows above its first

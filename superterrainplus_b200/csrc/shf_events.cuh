@@ -369,7 +369,11 @@ __global__ void __launch_bounds__(640, 1)
     constexpr uint32_t SS = emit_sbuf_stride(K, FW);
     constexpr uint32_t ACAP = emit_act_cap(K);
     constexpr int SR = emit_acc_regs(K, FW);
-    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = g.PW, stages = g.stages;
+    // Column segments (blockIdx.z; small calls only): this CTA emits the pixels [X0, X1) of its rows. Its columns are
+    // the segment's own window span [X0, X1 + 2r): the first 2r of them only fill the window, exactly like the first 2r
+    // columns of a whole row; PW, column indices and ring slots below are local to the segment.
+    const uint32_t X0 = blockIdx.z * g.cseg_px, X1 = min(g.W, X0 + g.cseg_px);
+    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = (X1 - X0) + two_r, stages = g.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
     const uint32_t y0 = tile * TY;
@@ -406,8 +410,8 @@ __global__ void __launch_bounds__(640, 1)
         const uint32_t bit0 = part * 128u;
         const uint32_t half = lane >> 4, lrow = lane & 15u;
         uint16_t* scr = reinterpret_cast<uint16_t*>(pscr_all) + (size_t)(warp - TY) * (2 * CPP * 16);
-        const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.P;
-        const uint8_t* base_tile = base + ((size_t)n_chunk * g.T + tile) * PW * CS + part * 16u;
+        const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.P + X0;
+        const uint8_t* base_tile = base + (((size_t)n_chunk * g.T + tile) * g.PW + X0) * CS + part * 16u;
         const uint32_t n_items = n_batches * PPB;
         uint32_t seg_n[SW];
         uint4 v_n = make_uint4(0u, 0u, 0u, 0u);
@@ -491,6 +495,15 @@ __global__ void __launch_bounds__(640, 1)
     const uint2* ev = pool + ri.x;
     const uint32_t E = (unsigned long long)ri.x + ri.y <= g.pool_cap ? ri.y : 0u;
     uint32_t off = row_active ? rowbase[(size_t)n_chunk * g.H + y] : 0u;  // offset of the next pixel's first bin
+    if (X0 != 0u && row_active) {
+        // bins of the row's pixels before this segment: every event contributes its overlap with [0, X0)
+        uint32_t before = 0u;
+        for (uint32_t i = lane; i < E; i += 32u) {
+            const uint32_t span_px = ev[i].y;
+            before += min(span_px >> 16, X0) - min(span_px & 0xFFFFu, X0);
+        }
+        off += __reduce_add_sync(kFull, before);
+    }
     uint2* dst = bins + (row_active ? (size_t)chunkbase[n_chunk] + off : (size_t)0);
     uint32_t* hso_row = hso + (size_t)n_chunk * ((size_t)g.W * g.H + 1u) + (size_t)(row_active ? y : 0u) * g.W;
     const float inv = g.inv_total;
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(640, 1)
             __syncwarp();
             // ---- the pixels of this batch: x = c - 2r ----
             if (ce > two_r) {
-                const uint32_t xa0 = cb > two_r ? cb - two_r : 0u, xe0 = ce - two_r;
+                const uint32_t xa0 = X0 + (cb > two_r ? cb - two_r : 0u), xe0 = X0 + ce - two_r;   // pixels of the row
                 uint32_t xa = xa0, xe = xe0;
                 bool single = false;
                 while (xa < xe0) {
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(640, 1)
                         }
                     }
                     // ---- emit the pixels [xa, xe) ----
-                    const uint8_t* sp = sb + (size_t)(xa + two_r - cb) * SS;  // window counts of pixel xa
+                    const uint8_t* sp = sb + (size_t)(xa - X0 + two_r - cb) * SS;  // window counts of pixel xa
                     if (pk_n) {
                         // lane = slot * Ea + entry: pk_n pixels per pass; positions by one ballot + popc
                         const uint32_t xb = ry[0] & 0xFFFFu, lim = min(ry[0] >> 16, xe), itm = rx[0] >> 16;

@@ -51,6 +51,7 @@ struct Geo {
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     uint32_t vseg, vseg_rows;      // vscan row segments per column block (1 = none) and output rows per segment (x32)
+    uint32_t cseg, cseg_px;        // emit column segments per row tile (1 = none) and pixels per segment (x16)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
     unsigned long long bins_cap, pool_cap;  // capacities of the bin buffer / event pool (guards of a speculative call)
 };

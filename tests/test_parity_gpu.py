@@ -237,6 +237,32 @@ def test_vscan_row_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segmen
         buf.close()
 
 
+@pytest.mark.parametrize("w,h,r,biomes,kind,segments", [
+    (300, 40, 8, 6, "rare", 4), (520, 33, 16, 30, "stripes", 8), (260, 96, 32, 12, "blocky", 3), (200, 64, 64, 5, "iid", 2),
+    (640, 20, 16, 70, "iid", 8), (400, 50, 100, 3, "blocky", 2), (530, 30, 130, 9, "stripes", 2), (700, 12, 4, 2, "rare", 8),
+    (333, 17, 32, 100, "iid", 5),
+])
+def test_emit_column_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segments, monkeypatch):
+    """Small calls split every row tile of the emitting kernel into column segments (each slides over the 2r columns before
+    its first pixel and starts its offsets after the bins of the pixels to its left): forced segment counts, the
+    planner's own choice and no segments must all agree with the oracle."""
+    rng = np.random.default_rng(w * 17 + h * 1009 + r)
+    nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
+    m = random_map(rng, w, h, biomes, kind, nn)
+    want = oracle_mod.run_port(m, (w, h), nn, r)
+    for setting in (str(segments), None, "off"):
+        if setting == "off":
+            monkeypatch.setenv("SHF_NO_CSEG", "1")
+        elif setting is None:
+            monkeypatch.delenv("SHF_DEBUG_CSEG", raising=False)
+        else:
+            monkeypatch.setenv("SHF_DEBUG_CSEG", setting)
+        buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+        got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+        assert_same(got, want, f"{w}x{h} r={r} B={biomes} {kind} column segments={setting}")
+        buf.close()
+
+
 def split_neighbours(m, w, h, nn):
     """The nn.x * nn.y chunk maps of a merged map, in local-index order (STPChunk::calcLocalChunkCoordinate)."""
     return [np.ascontiguousarray(m[cy * h:(cy + 1) * h, cx * w:(cx + 1) * w]) for cy in range(nn[1]) for cx in range(nn[0])]

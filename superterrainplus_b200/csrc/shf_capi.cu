@@ -571,7 +571,10 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         g.cseg_px = W;
         if (!generic && !getenv("SHF_NO_CSEG")) {
             const uint64_t ctas = (uint64_t)n_chunks * g.T;
-            uint32_t want = ctas < 2ull * (uint64_t)f->sm_count ? (uint32_t)((2ull * f->sm_count + ctas - 1u) / ctas) : 1u;
+            // (measured: 2 segments for 64..147 CTAs, 4 below; nothing to gain when one CTA fills an SM's shared memory)
+            uint32_t want = 2u * smem_of(ty) > f->smem_optin ? 1u
+                            : ctas * 2u <= (uint64_t)f->sm_count ? 4u
+                            : ctas < (uint64_t)f->sm_count ? 2u : 1u;
             if (const char* e = getenv("SHF_DEBUG_CSEG")) want = std::max(1u, (uint32_t)atoi(e));  // measurements only
             want = std::min(want, 8u);
             while (want > 1u) {

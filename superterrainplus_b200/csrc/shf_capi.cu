@@ -484,8 +484,10 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     const bool vec8 = (reinterpret_cast<uintptr_t>(in_dev) % 16u == 0u) && (in_row_stride % 8u == 0u) && (in_chunk_stride % 8u == 0u);
 
     // ---- same shape as the last call on this buffer: run with its plan, check afterwards ----
+    // (small calls only: a batch of hundreds of chunks does not notice two round trips, but would pay the check at the
+    // end of the call as a bubble before the next one)
     if (b->last_valid && b->last_g.W == W && b->last_g.H == H && b->last_g.r == r && b->last_g.n_chunks == n_chunks &&
-        !getenv("SHF_NO_SPECULATION")) {
+        (uint64_t)n_chunks * W * H <= (16ull << 20) && !getenv("SHF_NO_SPECULATION")) {
         Geo gs = b->last_g;
         gs.in_row_stride = in_row_stride;
         gs.in_chunk_stride = in_chunk_stride;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Randomised differential test on a GPU: random shapes, radii (8-bit ring, 16-bit ring, wide path), biome counts
-(K = 1..8 and beyond), map kinds and batch sizes against the CPU oracle, bit for bit. usage: python tests/fuzz_gpu.py [cases] [seed]
+(K = 1..8 and beyond), map kinds and batch sizes against the CPU oracle, bit for bit. usage: python tests/fuzz_gpu.py [cases] [seed] [big]
 (test infrastructure: run by tests/test_fuzz_gpu.py; the oracle is the checker)"""
 import os, sys, time
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -13,6 +13,7 @@ from helpers import assert_same
 from test_parity_gpu import random_map
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+big = len(sys.argv) > 3 and sys.argv[3] == "big"   # larger maps: the row / column segmented kernels of small calls
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 12345)
 filt = shf.STPSingleHistogramFilter()
 FB = shf.STPSingleHistogramFilter.STPFilterBuffer
@@ -21,13 +22,13 @@ kinds = ["iid", "blocky", "rare", "stripes", "hstripes"]
 plans = {}
 t0 = time.time()
 for case in range(n_cases):
-    w, h = int(rng.integers(4, 200)), int(rng.integers(4, 160))
+    w, h = (int(rng.integers(4, 200)), int(rng.integers(4, 160))) if not big else (int(rng.integers(64, 700)), int(rng.integers(64, 600)))
     rmax = int(rng.choice([16, 64, 126, 200, 254, 300]))
     r = 2 * int(rng.integers(1, rmax // 2 + 1))
     biomes = int(rng.choice([1, 2, 5, 20, 33, 64, 65, 100, 129, 200, 256, 257, 400]))
     kind = kinds[int(rng.integers(0, len(kinds)))]
     nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
-    if (w * nn[0]) * (h * nn[1]) > 1_500_000:   # keep the oracle quick
+    if (w * nn[0]) * (h * nn[1]) > (1_500_000 if not big else 6_000_000):   # keep the oracle quick
         continue
     n = int(rng.choice([1, 1, 2, 3]))
     maps = [random_map(rng, w, h, biomes, kind, nn) for _ in range(n)]

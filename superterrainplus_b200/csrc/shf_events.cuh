@@ -528,6 +528,15 @@ __global__ void __launch_bounds__(640, 1)
         mbar_wait(&full_bar[s], (b / stages) & 1u);
         if (row_active) {
             // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
+            if (cb >= span && ce - cb == (uint32_t)NB && in_slot + NB <= R && out_slot + NB <= R) {
+                // the steady state: a whole batch, no ring wrap, every column has a leaving partner and a pixel
+                slide_cols<K, FW, true, true>(crow + in_slot * CS + lane * (K * FW / 8), crow + out_slot * CS + lane * (K * FW / 8),
+                                              sb + lane * (FW == 8 ? 2 * K : 4 * K), (uint32_t)NB, srun);
+                in_slot += NB;
+                if (in_slot >= R) in_slot -= R;
+                out_slot += NB;
+                if (out_slot >= R) out_slot -= R;
+            } else
             for (uint32_t c = cb; c < ce;) {
                 // a segment: no ring wrap, the leaving column exists or not, pixels are due or not
                 const bool has_out = c >= span, st = c >= two_r;

@@ -630,7 +630,27 @@ __global__ void __launch_bounds__(640, 1)
                         const uint32_t vid = rx[0] & 0xFFFFu;
                         const uint32_t sa_step = pk_n * SS;
                         uint32_t* hp = hso_row + x;
-                        for (uint32_t xp = xa; xp < xe; xp += pk_n) {
+                        uint32_t xp = xa;
+                        if (clean) {
+                            // every listed event is alive for every pixel of the range: a full pass writes pk_n * Ea
+                            // bins, lane = position, no vote needed
+                            const uint32_t full = pk_n * Ea;
+                            const bool writer = lane < full, marks = pk_entry == 0u && pk_slot < pk_n;
+                            const uint32_t hoff = pk_slot * Ea;
+                            for (; xp + pk_n <= xe; xp += pk_n) {
+                                if (writer) {
+                                    const uint32_t cnt = staged_count<FW>(sa, vid);
+                                    dst[lane] = make_uint2(itm, __float_as_uint(__fmul_rn(__uint2float_rn(cnt), inv)));
+                                }
+                                if (marks) *hp = off + hoff;
+                                dst += full;
+                                off += full;
+                                x += pk_n;
+                                sa += sa_step;
+                                hp += pk_n;
+                            }
+                        }
+                        for (; xp < xe; xp += pk_n) {
                             const bool alive = x - xb < len;
                             const unsigned bm = __ballot_sync(kFull, alive);
                             const uint32_t pos = (uint32_t)__popc(bm & lanemask_lt());

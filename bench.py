@@ -6,8 +6,10 @@
 A "step" is one pass of the filter over one batch of synthetic chunk neighbourhoods. The default workload is C3, the
 configuration BASELINE.json quotes its scaling target on: 256 neighbourhoods (3x3 chunks of 512x512 uint16 biome ids),
 radius 64, 64 biomes; biome ids iid uniform like the reference's own benchmark (STPTestHistogram.cpp:342-343). With N > 1
-(torchrun, one rank per GPU) every rank filters its own 256-chunk batch: independent units, no collective on the data
-path, weak scaling; `value` = pixels of all ranks / max-over-ranks device time.
+(torchrun, one rank per GPU) the ONE 256-chunk batch is sharded contiguously, 256/N chunks per rank, the way the
+reference's filterDistributed splits one job over its workers (SHF.cpp:789-868): independent units, halos replicated,
+no collective on the data path, STRONG scaling (`--scaling weak` gives every rank its own full batch instead);
+`value` = pixels of all ranks / max-over-ranks device time.
 
 Printed keys beyond the base contract:
   roofline      the emitting kernel (emit_kernel<K>): algorithmic bytes of the step / its CUDA-event duration vs the measured HBM peak
@@ -16,6 +18,10 @@ Printed keys beyond the base contract:
                 bounded sample of the same chunks (N=1 only)
   e2e           same metric through shf_run_batch with HOST buffers: H2D of the inputs and D2H of bins + offsets inside
                 the timed region, sub-batches on two host threads so copies overlap compute
+  parity_checked  sampled chunks of the TIMED result (downloaded after the timed region) compared bit for bit with the
+                reference CPU filter (oracle/_ref, else the C restatement)
+  consumer      the device-side heightfield consumer on the resident result (filter -> heightfield, no host round trip)
+  config4_chain BASELINE.json config 4 on its own shape: one 2048x2048 chunk, filter -> heightfield on device (N=1 only)
 `--impl reference` times the reference CPU filter alone (all host cores) on the same workload definition.
 """
 from __future__ import annotations
@@ -61,15 +67,22 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=0, help="override the number of chunks per GPU (debugging)")
     ap.add_argument("--radius", type=int, default=0, help="override the radius (BASELINE.json config 5 sweeps)")
     ap.add_argument("--biomes", type=int, default=0, help="override the biome count (BASELINE.json config 5 sweeps)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every GPU filters its own batch of the workload's size; strong: one batch is sharded")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (BASELINE.json config 3): one batch is sharded over the GPUs; weak: every GPU filters "
+                         "its own batch of the workload's size")
+    ap.add_argument("--min-seconds", type=float, default=0.0,
+                    help="raise --steps so that the timed region lasts at least this long (single-call workloads: the "
+                         "clock sampler needs a few 50 ms samples inside it)")
+    ap.add_argument("--parity-chunks", type=int, default=4, help="chunks of the timed result checked against the CPU filter")
+    ap.add_argument("--no-consumer", action="store_true")
+    ap.add_argument("--sync-steps", action="store_true",
+                    help="time the host-blocking shf_run_device instead of back-to-back shf_run_device_async calls")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-sub", type=int, default=32, help="chunks per shf_run_batch call in the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--heightfield", action="store_true",
-                    help="also time the device-side consumer (multi-biome heightfield) on the resident histograms")
+    ap.add_argument("--heightfield", action="store_true", help="(kept for old scripts: the consumer leg now always runs)")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
                     help="torch.distributed backend of the barrier / max-over-ranks plumbing (no data-path collective)")
     return ap.parse_args()
@@ -98,13 +111,19 @@ def shard_of(rank, world, chunks, scaling):
     return first, min(per, chunks - first)
 
 
-def config_of(wl, n_gpus):
+def config_of(wl, n_gpus, scaling):
+    """The same dictionary for both arms (`wl` = the workload as named, before sharding)."""
+    per_gpu = wl.chunks if scaling == "weak" else (wl.chunks + n_gpus - 1) // n_gpus
+    out_mb = per_gpu * wl.map_size[0] * wl.map_size[1] * 12 / 1e6  # >= one bin + one offset per pixel
     return {
         "workload": f"{wl.name}: {wl.chunks} x (3x3 neighbourhood of {wl.map_size[0]}x{wl.map_size[1]} uint16 maps), "
                     f"radius {wl.radius}, {wl.biomes} biomes, {wl.dist} ids",
-        "chunks_per_gpu": wl.chunks, "map": list(wl.map_size), "radius": wl.radius, "biomes": wl.biomes,
-        "distribution": wl.dist, "sharding": f"chunk batch x{n_gpus}, halos replicated, no collective",
-        "l2": "inputs + outputs per step far exceed the 126 MB L2 (no flush needed)",
+        "chunks_total": wl.chunks * (n_gpus if scaling == "weak" else 1), "chunks_per_gpu": per_gpu,
+        "map": list(wl.map_size), "radius": wl.radius, "biomes": wl.biomes, "distribution": wl.dist,
+        "sharding": (f"one {wl.chunks}-chunk batch split into {n_gpus} contiguous shards" if scaling == "strong"
+                     else f"{n_gpus} x {wl.chunks}-chunk batches") + ", halos replicated, no collective",
+        "l2": ("outputs per step exceed the 126 MB L2 (no flush needed)" if out_mb > 126.0 else
+               "outputs per step fit the 126 MB L2: a 256 MB buffer is rewritten between steps"),
     }
 
 
@@ -264,9 +283,9 @@ def run_reference_arm(args):
     last["value"] = value
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic", "impl": "reference",
-        "config": config_of(wl, args.gpus), "cpu_baseline": last,
+        "config": config_of(wl, args.gpus, args.scaling), "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -310,6 +329,95 @@ def bind_to_gpu_numa_node(local):
 
 
 
+def download_chunk(buf, chunk, w, h):
+    """(items, weights, offsets) of one chunk of the buffer's device-resident result, copied to the host."""
+    import torch
+
+    from superterrainplus_b200 import api
+
+    bins_p, offs_p = buf.readDevice()
+    base = buf.chunkBase()
+    lo, hi = int(base[chunk]), int(base[chunk + 1])
+    per = w * h + 1
+    raw = torch.as_tensor(api.DeviceArrayView(bins_p + lo * 8, 2 * (hi - lo)), device="cuda").cpu().numpy()
+    offs = torch.as_tensor(api.DeviceArrayView(offs_p + chunk * per * 4, per), device="cuda").cpu().numpy()
+    bins = raw.view(api.BIN_DTYPE)
+    return bins["Item"].copy(), bins["Weight"].copy(), offs.view(np.uint32).copy()
+
+
+def check_against_cpu_filter(wl, host_map, got):
+    """Bit-exact comparison of one chunk with the reference CPU filter (the oracle as the checker, never as the product)."""
+    import oracle
+
+    if oracle.have_reference():
+        sess = oracle.ReferenceSession(0xFF)
+        items, weights, offsets = sess.run(host_map, wl.map_size, wl.nn, wl.radius, wl.total)
+        sess.close()
+        kind = "reference"
+    else:
+        items, weights, offsets = oracle.run_port(host_map, wl.map_size, wl.nn, wl.radius)
+        kind = "port"
+    ok = (np.array_equal(got[2], offsets) and np.array_equal(got[0], items)
+          and np.array_equal(got[1].view(np.uint32), weights.view(np.uint32)))
+    return bool(ok), kind
+
+
+def heightfield_generator(pkg, api, filt, biomes):
+    rng = np.random.default_rng(7)
+    table = np.zeros(biomes, dtype=api.BIOME_PROPERTY_DTYPE)
+    table["Scale"], table["Octave"] = rng.uniform(100.0, 900.0, biomes), 8
+    table["Persistence"], table["Lacunarity"] = 0.5, 2.0
+    table["Depth"], table["Variation"] = rng.uniform(0.0, 1.0, biomes), rng.uniform(0.1, 1.0, biomes)
+    perm = np.tile(rng.permutation(256).astype(np.uint8), 2)
+    ang = np.arange(12) * (2 * np.pi / 12)
+    return pkg.STPMultiBiomeHeightfield(filt, table, perm, np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32))
+
+
+def config4_chain(pkg, api, workloads, filt, local, stream, steps=8):
+    """BASELINE.json config 4 on its own shape: one 2048x2048 chunk (3x3 neighbourhood, radius 64, 32 biomes) filtered and
+    fed to the multi-biome heightfield kernel where the filter left the histogram in HBM -- no host round trip of bins or
+    offsets (the copy + sync of STPBiomefieldGenerator.cpp:108-123 is gone). Device time per chunk, CUDA events."""
+    import torch
+
+    out = {}
+    FB = pkg.STPSingleHistogramFilter.STPFilterBuffer
+    for dist in ("uniform", "blocky"):
+        wl = dataclasses.replace(workloads.CONFIGS["C4"], dist=dist)
+        w, h = wl.map_size
+        tw, th = wl.total
+        info = pkg.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total)
+        maps = workloads.make_maps_torch(wl, 0, 1, torch.device("cuda", local))
+        buf = FB(FB.STPExecutionType.Parallel)
+        gen = heightfield_generator(pkg, api, filt, wl.biomes)
+        heights = torch.empty((1, h, w), dtype=torch.float32, device="cuda")
+        offs = np.zeros((1, 2), dtype=np.float32)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        for i in range(3 + steps):
+            flush.fill_(i & 0xFF)
+            k = i - 3
+            if k >= 0:
+                ev[k][0].record()
+            filt.runDeviceAsync(maps.data_ptr(), th * tw, 1, info, buf, wl.radius, stream)
+            if k >= 0:
+                ev[k][1].record()
+            gen(buf, 0, 1, offs, heights.data_ptr(), stream)   # completes the filter call, then enqueues the consumer
+            if k >= 0:
+                ev[k][2].record()
+        torch.cuda.synchronize()
+        f_ms = statistics.median(e[0].elapsed_time(e[1]) for e in ev)
+        c_ms = statistics.median(e[0].elapsed_time(e[2]) for e in ev)
+        n_bins, _ = buf.size()
+        out[dist] = {"filter_ms": f_ms, "chain_ms": c_ms, "chain_mpixels_per_s": w * h / (c_ms * 1e-3) / 1e6,
+                     "bins_per_pixel": n_bins / (w * h), "heights_finite": bool(torch.isfinite(heights).all().item())}
+        gen.close()
+        buf.close()
+        del maps, heights, flush
+    out["what"] = ("one 2048x2048 chunk, radius 64, 32 biomes: shf_run_device_async -> shf_heightfield_run on the "
+                   "device-resident histogram, 8 octaves per bin; L2 flushed between iterations")
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -343,11 +451,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    wl = workload_of(args)
+    wl_named = workload_of(args)
+    wl = wl_named
     w, h = wl.map_size
     tw, th = wl.total
     first_chunk, n = shard_of(rank, world, wl.chunks, args.scaling)
     total_chunks = wl.chunks * world if args.scaling == "weak" else wl.chunks
+    if n == 0:
+        raise SystemExit("bench.py: more ranks than chunks")
     wl = dataclasses.replace(wl, chunks=n)
     info = pkg.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total)
     maps = workloads.make_maps_torch(wl, first_chunk, n, torch.device("cuda", local))
@@ -359,75 +470,111 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     api.set_profiling(True)
 
+    # A step = one pass of the filter over this rank's shard, inputs resident in HBM. Steps are enqueued back to back
+    # (shf_run_device_async); the plan checks of the last one are made by buf.wait() inside the timed region.
     def step():
-        filt.runDevice(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
+        if args.sync_steps:
+            filt.runDevice(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
+        else:
+            filt.runDeviceAsync(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_w0 = time.perf_counter()
     for _ in range(args.warmup):
         step()
+    repeated0 = buf.wait()
     torch.cuda.synchronize()
+    est = (time.perf_counter() - t_w0) / max(1, args.warmup)
     n_bins, _ = buf.size()
     plan = buf.lastPlan()
+    alg_bytes = workloads.algorithmic_bytes(wl, n_bins)
+    steps = args.steps
+    if args.min_seconds > 0.0:
+        steps = max(steps, int(args.min_seconds / max(est, 1e-5)) + 1)
+        steps = int(max_over_ranks(float(steps)))
+    # outputs that fit the L2: rewrite a buffer larger than the L2 between steps and time every step on its own
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if alg_bytes < (126 << 20) else None
 
-    phases = []
     api.stats_reset()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        buf.wait()
+        e1.record()
+        barrier()
+        ms_local = e0.elapsed_time(e1) / steps
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            evs[i][0].record()
+            step()
+            evs[i][1].record()
+        buf.wait()
+        barrier()
+        ms_local = sum(a.elapsed_time(b_) for a, b_ in evs) / steps
     t_wall1 = time.time()
+    repeated = buf.wait() - repeated0
     # the phase events of the timed steps, read back after the timed region (no host synchronisation inside it)
-    phases = [buf.phaseMs(back) for back in range(min(args.steps, 64))]
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    phases = [buf.phaseMs(back) for back in range(min(steps, 64))]
+    ms_step = max_over_ranks(ms_local)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     launches, _, _ = api.stats()
     api.set_profiling(False)
     value = total_chunks * w * h / (ms_step * 1e-3) / 1e6
 
     phases_ms = {k: statistics.median(p[k] for p in phases) for k in phases[0]}
-    alg_bytes = workloads.algorithmic_bytes(wl, n_bins)
     peak, peak_src = measured_peak()
     emit_ms = phases_ms["emit"]
     achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "emit_kernel<K>" if plan["k_sets"] else "march_generic_kernel<emit>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic("emit_kernel", wl, n), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
-                "whole_step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
+                "whole_step_frac": alg_bytes / (ms_local * 1e-3) / 1e9 / peak}
+
+    # ---- the timed result itself against the reference CPU filter: sampled chunks, downloaded after the timed region ----
+    parity = None
+    if rank == 0 and args.parity_chunks > 0:
+        picks = sorted({0, n - 1, n // 3, (2 * n) // 3})[:args.parity_chunks]
+        oks, kind = [], None
+        for c in picks:
+            ok, kind = check_against_cpu_filter(wl, maps[c].cpu().numpy(), download_chunk(buf, c, w, h))
+            oks.append(ok)
+        parity = {"chunks": [first_chunk + c for c in picks], "ok": all(oks), "against": kind,
+                  "compared": "items, offsets, weight bits of every pixel of the sampled chunks"}
+        if not all(oks):
+            raise SystemExit(f"bench.py: the timed result differs from the CPU filter on chunks {picks}: {oks}")
 
     # ---- device-side consumer on the resident result (BASELINE.json config 4 chain) ----
     consumer = None
-    if args.heightfield:
-        rng = np.random.default_rng(7)
-        table = np.zeros(wl.biomes, dtype=api.BIOME_PROPERTY_DTYPE)
-        table["Scale"], table["Octave"] = rng.uniform(100.0, 900.0, wl.biomes), 8
-        table["Persistence"], table["Lacunarity"] = 0.5, 2.0
-        table["Depth"], table["Variation"] = rng.uniform(0.0, 1.0, wl.biomes), rng.uniform(0.1, 1.0, wl.biomes)
-        perm = np.tile(rng.permutation(256).astype(np.uint8), 2)
-        ang = np.arange(12) * (2 * np.pi / 12)
-        gen = pkg.STPMultiBiomeHeightfield(filt, table, perm, np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32))
-        heights = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
-        offs = np.zeros((n, 2), dtype=np.float32)
+    if not args.no_consumer:
+        gen = heightfield_generator(pkg, api, filt, wl.biomes)
+        nc = min(n, 32)   # heights of at most 32 chunks per consumer launch measured (the kernel is compute-bound)
+        heights = torch.empty((nc, h, w), dtype=torch.float32, device="cuda")
+        offs = np.zeros((nc, 2), dtype=np.float32)
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(3 + args.steps):
-            if i == 3:
+        c_steps = 3
+        for i in range(1 + c_steps):
+            if i == 1:
                 h0.record()
-            for first in range(0, n, 65535):
-                cnt = min(65535, n - first)
-                gen(buf, first, cnt, offs[first:first + cnt], heights[first].data_ptr(), stream)
+            gen(buf, 0, nc, offs, heights.data_ptr(), stream)
         h1.record()
         torch.cuda.synchronize()
-        hms = h0.elapsed_time(h1) / args.steps
+        hms = h0.elapsed_time(h1) / c_steps * (n / nc)
         consumer = {"kernel": "heightfield_kernel", "ms": hms, "mpixels_per_s": n * w * h / (hms * 1e-3) / 1e6,
-                    "octaves": 8, "bins_per_pixel": n_bins / (n * w * h),
-                    "chain_ms": ms_step + hms, "chain_mpixels_per_s": n * w * h / ((ms_step + hms) * 1e-3) / 1e6}
+                    "octaves": 8, "bins_per_pixel": n_bins / (n * w * h), "chunks_measured": nc,
+                    "chain_ms": ms_local + hms, "chain_mpixels_per_s": n * w * h / ((ms_local + hms) * 1e-3) / 1e6}
         gen.close()
         del heights
+    c4 = None
+    if rank == 0 and world == 1 and not args.no_consumer:
+        c4 = config4_chain(pkg, api, workloads, filt, local, stream)
 
     # ---- end to end: host buffers in, page-locked host histograms out ----
     e2e = None
@@ -492,6 +639,7 @@ def run_ours(args):
         e2e = {"value": total_chunks * w * h / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "d2h_gb_per_s": d2h_total / dt / 1e9,
                "how": f"shf_run_batch on pinned host maps, {sub} chunks per call, {n_threads} host threads with one "
                       "filter buffer each; bins + offsets copied to page-locked host memory inside the timed region",
                "gpu_launches_per_step": sum(m[0] for m in moved)}
@@ -506,12 +654,16 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u16 samples, u32 counts, f32 weights", "data": "synthetic",
-            "config": {**config_of(wl, world), "plan": plan, "bins_per_pixel": n_bins / (n * w * h)},
-            "roofline": roofline, "phases_ms": phases_ms, "cpu_baseline": cpu, "e2e": e2e, "consumer": consumer,
-            "host_numa_node_rank0": numa,
+            "config": config_of(wl_named, world, args.scaling),
+            "plan": plan, "bins_per_pixel": n_bins / (n * w * h),
+            "step_call": "shf_run_device (host-blocking)" if args.sync_steps else
+                         "shf_run_device_async back to back + shf_buffer_wait inside the timed region",
+            "calls_repeated_on_checked_path": repeated,
+            "roofline": roofline, "phases_ms": phases_ms, "parity_checked": parity, "cpu_baseline": cpu, "e2e": e2e,
+            "consumer": consumer, "config4_chain": c4, "host_numa_node_rank0": numa,
             "gpu_launches": launches, "clocks": clocks, "impl": "ours",
         }
         emit(line)

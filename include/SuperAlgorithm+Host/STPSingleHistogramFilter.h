@@ -79,6 +79,10 @@ namespace SuperTerrainPlus::STPAlgorithm {
 			//index of the first bin of chunk `chunk` of the last batch result; chunkOffset(chunk count) = total bins
 			std::uint64_t chunkOffset(unsigned int chunk) const;
 
+			//completes a pending filterDeviceAsync (every other query of the result does so as well); returns how many
+			//calls on this buffer ran ahead with a plan that did not fit their input and were repeated so far
+			std::uint64_t wait();
+
 		};
 
 	private:
@@ -132,6 +136,13 @@ namespace SuperTerrainPlus::STPAlgorithm {
 		//merged maps already in device memory (chunk i at samplemap_device + i * chunk_stride samples); the result stays
 		//in device memory (readDeviceHistogram). `stream` is a cudaStream_t; the call returns once the work is enqueued.
 		void filterDevice(const STPSample_t* samplemap_device, std::uint64_t chunk_stride, unsigned int chunk_count,
+			const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int radius, void* stream = nullptr);
+
+		//filterDevice without any host synchronisation when the shape equals that of the last completed call on the buffer:
+		//the work is enqueued on `stream` with the previous call's plan, the first query of the result (wait(), size(),
+		//readDeviceHistogram(), ...) checks it and repeats the call when the plan did not fit -- `samplemap_device` must
+		//stay unchanged until then
+		void filterDeviceAsync(const STPSample_t* samplemap_device, std::uint64_t chunk_stride, unsigned int chunk_count,
 			const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int radius, void* stream = nullptr);
 
 	};

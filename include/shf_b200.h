@@ -91,11 +91,31 @@ SHF_API int shf_run_batch(shf_filter* filter, const uint16_t* const* samplemaps,
 
 /* Device-resident variant: samplemaps_dev points at n_chunks merged maps in DEVICE memory, chunk i starting at
  * samplemaps_dev + i * chunk_stride (in samples). The result stays in device memory (shf_buffer_read_device); nothing is
- * copied to the host except per-chunk bin totals. `stream` is a cudaStream_t (NULL = the legacy default stream); the
- * call returns after the last kernel has been enqueued on it. */
+ * copied to the host except per-chunk distinct-value counts and bin totals. `stream` is a cudaStream_t (NULL = the
+ * legacy default stream). The call BLOCKS THE HOST: the first call of a shape waits for the stream twice (plan, bin
+ * buffer size) and returns with the emitting kernel still in flight; a repeated call of the same shape on the same
+ * buffer runs ahead with the previous plan and waits once, at its end, to check it. It may free and reallocate device
+ * scratch, so it cannot be stream-captured. A later call on the same buffer from another stream waits (on the device)
+ * for the work this one left in flight. */
 SHF_API int shf_run_device(shf_filter* filter, const uint16_t* samplemaps_dev, uint64_t chunk_stride, uint32_t n_chunks,
                            const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
                            const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius, void* stream);
+
+/* The same without any host synchronisation when the call can run ahead (same shape as the last COMPLETED call on this
+ * buffer; otherwise it behaves like shf_run_device): everything is enqueued on `stream` and the call returns. The
+ * checks of the plan it ran with are made by the first query of the result -- shf_buffer_wait, shf_buffer_size,
+ * shf_buffer_read_device, shf_buffer_chunk_base, shf_heightfield_run -- which waits for the call; if the input needed
+ * another plan or larger buffers, that query repeats the call on the checked path, so `samplemaps_dev` must stay
+ * unchanged until then (or until the next call on the buffer, which simply replaces the pending one). Back-to-back
+ * calls on one stream therefore keep the device busy without a bubble between them. */
+SHF_API int shf_run_device_async(shf_filter* filter, const uint16_t* samplemaps_dev, uint64_t chunk_stride,
+                                 uint32_t n_chunks, const uint32_t map_size[2], const uint32_t nearest_neighbour[2],
+                                 const uint32_t total_map_size[2], shf_buffer* buffer, uint32_t radius, void* stream);
+/* Completes a pending shf_run_device_async on the buffer and returns its status (SHF_OK at once when nothing is
+ * pending). On return the result is complete in stream order (a repeated call may still have its emitting kernel in
+ * flight on the call's stream). repeated_calls (optional): how many calls on this buffer ran ahead with a plan that did
+ * not fit and were repeated so far -- work enqueued behind such a call read a discarded result and must be re-issued. */
+SHF_API int shf_buffer_wait(shf_buffer* buffer, uint64_t* repeated_calls);
 
 /* n_calls concurrent operator() calls served by ONE pass over the device (the world
  * pipeline runs up to five STPBiomefieldGenerator::operator() at once, SuperDemo+/World/Biomes/

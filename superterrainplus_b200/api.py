@@ -32,7 +32,7 @@ SHF_ERR_OFFSET_OVERFLOW, SHF_ERR_UNSUPPORTED, SHF_ERR_INVALID_ARGUMENT = 4, 5, 6
 # every symbol include/shf_b200.h declares (tests check the library exports exactly these)
 C_ABI_SYMBOLS = (
     "shf_filter_create", "shf_filter_destroy", "shf_buffer_create", "shf_buffer_destroy", "shf_buffer_read",
-    "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_run_neighbours",
+    "shf_buffer_size", "shf_buffer_type", "shf_run", "shf_run_batch", "shf_run_device", "shf_run_device_async", "shf_buffer_wait", "shf_run_neighbours",
     "shf_run_neighbours_device", "shf_run_multi", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
     "shf_set_profiling", "shf_buffer_phase_ms", "shf_buffer_phase_history", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
@@ -94,6 +94,8 @@ def library() -> ctypes.CDLL:
     lib.shf_run.argtypes = [vp, vp, _U32x2, _U32x2, _U32x2, vp, u32]
     lib.shf_run_batch.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, _U32x2, vp, u32]
     lib.shf_run_device.argtypes = [vp, vp, u64, u32, _U32x2, _U32x2, _U32x2, vp, u32, vp]
+    lib.shf_run_device_async.argtypes = [vp, vp, u64, u32, _U32x2, _U32x2, _U32x2, vp, u32, vp]
+    lib.shf_buffer_wait.argtypes = [vp, P(u64)]
     lib.shf_run_neighbours.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32]
     lib.shf_run_multi.argtypes = [vp, P(vp), P(vp), u32, _U32x2, _U32x2, _U32x2, u32]
     lib.shf_run_neighbours_device.argtypes = [vp, P(vp), u32, _U32x2, _U32x2, vp, u32, vp]
@@ -151,6 +153,15 @@ class STPSingleHistogram:
 
     Bin: Optional[np.ndarray]
     HistogramStartOffset: Optional[np.ndarray]
+
+
+class DeviceArrayView:
+    """A raw device pointer dressed as a CUDA array (``__cuda_array_interface__``), so that torch / cupy can wrap the
+    device-resident result without a copy: ``torch.as_tensor(DeviceArrayView(ptr, n, "<i4"), device="cuda")``."""
+
+    def __init__(self, ptr: int, count: int, typestr: str = "<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
 
 
 def set_profiling(enabled: bool) -> None:
@@ -230,6 +241,13 @@ class STPSingleHistogramFilter:
             if not p.value:
                 return np.zeros(0, dtype=np.uint64)
             return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), (n.value + 1,)).copy()
+
+        def wait(self) -> int:
+            """Completes a pending runDeviceAsync (shf_buffer_wait); returns how many calls on this buffer ran ahead with
+            a plan that did not fit and were repeated so far."""
+            n = ctypes.c_uint64()
+            _check(library().shf_buffer_wait(self._h, ctypes.byref(n)))
+            return n.value
 
         def phaseMs(self, back: int = 0) -> dict:
             """Milliseconds of every kernel phase of the last call, or of the call `back` calls before it (the last 64
@@ -332,6 +350,15 @@ class STPSingleHistogramFilter:
         _check(library().shf_run_device(self._h, device_ptr, chunk_stride, n_chunks, _U32x2(*nn_info.MapSize),
                                         _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
                                         filter_buffer._h, radius, stream))
+
+
+    def runDeviceAsync(self, device_ptr: int, chunk_stride: int, n_chunks: int, nn_info: STPNearestNeighbourInformation,
+                       filter_buffer: "STPFilterBuffer", radius: int, stream: int = 0) -> None:
+        """runDevice without host synchronisation when the call can run ahead (shf_run_device_async); the first query of
+        the result (filter_buffer.wait(), size(), readDevice(), ...) completes it."""
+        _check(library().shf_run_device_async(self._h, device_ptr, chunk_stride, n_chunks, _U32x2(*nn_info.MapSize),
+                                              _U32x2(*nn_info.ChunkNearestNeighbour), _U32x2(*nn_info.TotalMapSize),
+                                              filter_buffer._h, radius, stream))
 
 
 STPFilterBuffer = STPSingleHistogramFilter.STPFilterBuffer

@@ -23,6 +23,21 @@ volatile int g_profiling = 0;  // shf_set_profiling: record CUDA events between 
 constexpr int kEvRing = 64;    // profiled calls whose phase events are kept per buffer (read back without a sync per call)
 constexpr int kPhases = 6;     // dictionary | remap + vscan | event lists | row scan | host gap | emit
 
+// The reference's operator() never touches the calling thread's CUDA device; every entry point that binds the filter's
+// device restores the caller's on the way out.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int device) : want(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int fail(int status, const char* expr, const std::string& what) {
     tls_error = std::string(expr) + ": " + what;
     return status;
@@ -89,14 +104,22 @@ struct PinBuf {
 
 }  // namespace
 
+// measurement toggles, read once when the filter is created (never needed for correctness)
+struct shf_toggles {
+    bool no_speculation = false, no_cseg = false, no_vseg = false;
+    uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0;  // 0 = not set
+};
+
 struct shf_filter {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    shf_toggles dbg;
 };
 
 struct shf_heightfield {
     int device = 0;
+    int sm_count = 0;
     size_t smem_optin = 0;
     uint32_t n_table = 0, grad_size = 0;
     DevBuf table, perm, grad;
@@ -120,6 +143,19 @@ struct shf_buffer {
     // away and checks afterwards (run_speculative)
     shf::Geo last_g{};
     bool last_valid = false;
+    // a call that ran ahead of its checks (enqueue_speculative) and what settle() needs to complete or repeat it
+    struct Deferred {
+        bool active = false;
+        shf_filter filt{};
+        shf::Geo g{};
+        const uint16_t* in_dev = nullptr;
+        bool vec8 = false;
+        cudaStream_t stream = nullptr;
+    } deferred;
+    cudaEvent_t done_ev = nullptr;      // recorded behind the last operation of every call, on the call's stream
+    cudaStream_t done_stream = nullptr;
+    bool done_recorded = false;
+    uint64_t spec_misses = 0;           // calls that ran ahead with a plan that did not fit and were repeated
     cudaEvent_t ev[kEvRing][kPhases + 1] = {};
     uint64_t ev_calls = 0;   // profiled calls so far; call c uses ring slot c % kEvRing
     bool ev_valid = false;
@@ -142,6 +178,10 @@ struct shf_buffer {
         ev_valid = false;
         ev_calls = 0;
         last_valid = false;
+        deferred.active = false;
+        if (done_ev) cudaEventDestroy(done_ev);
+        done_ev = nullptr;
+        done_recorded = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
                        &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
                        &evpool, &rowinfo, &cvt, &vexit};
@@ -160,8 +200,8 @@ using shf::Geo;
 
 // CTAs per chunk of the row-streaming kernels (dictionary, remap): about 8 CTAs per SM over the whole batch; every CTA
 // carries a fixed cost (zeroing / loading 8-16 KB of tables), so large batches use few CTAs per chunk
-uint32_t shf_rows_grid(uint32_t PH, uint32_t n_chunks) {
-    const uint32_t want = (8u * 148u + n_chunks - 1u) / n_chunks;
+uint32_t shf_rows_grid(uint32_t PH, uint32_t n_chunks, int sm_count) {
+    const uint32_t want = (8u * (uint32_t)sm_count + n_chunks - 1u) / n_chunks;
     return std::max(1u, std::min(std::min(want, PH), 256u));
 }
 
@@ -270,7 +310,7 @@ int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) 
 }
 
 // scratch every path needs + the compact-id map and the dictionary
-int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
+int prepare_common(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
     const size_t cells = (size_t)g.n_chunks * g.PH * g.P;
     SHF_CUDA(b->cmap.ensure(cells * 2 + 64));  // producers read whole 16/32-byte row segments
     SHF_CUDA(b->dict.ensure((size_t)g.n_chunks * g.Bpad * 2));
@@ -279,7 +319,7 @@ int prepare_common(shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec
     SHF_CUDA(b->chunktotal.ensure((size_t)(g.n_chunks + 1) * 8));  // + the event counter
     SHF_CUDA(b->chunkbase.ensure((size_t)(g.n_chunks + 1) * 8));
     SHF_CUDA(b->hso.ensure((size_t)g.n_chunks * ((size_t)g.W * g.H + 1u) * 4));
-    const dim3 pgrid(shf_rows_grid(g.PH, g.n_chunks), g.n_chunks);
+    const dim3 pgrid(shf_rows_grid(g.PH, g.n_chunks, f->sm_count), g.n_chunks);
     if (vec8)
         shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
                                                    b->cmap.as<uint16_t>(), b->dict.as<uint16_t>(), g.Bpad);
@@ -354,7 +394,7 @@ int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_d
         return fail(SHF_ERR_UNSUPPORTED, "per-row tables fit shared memory", "radius x biome count too large for one CTA");
     b->plan_smem = (uint32_t)smem;
     SHF_CUDA(b->vstart.ensure((size_t)g.n_chunks * g.PH * g.P * 2));
-    int st = prepare_common(b, g, in_dev, vec8, s);
+    int st = prepare_common(f, b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
     // vertical chain starts; per-(biome, column) state for a sub-batch of chunks at a time (<= 1 GiB of scratch)
     const size_t per_chunk = (size_t)nb * g.PW * 4;
@@ -389,23 +429,21 @@ int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_d
     return publish(b, g);
 }
 
-constexpr int kSpecMiss = -1000;  // run_speculative: the guess did not hold, take the checked path
-
 // A repeated call of the same shape on the same buffer (the pipeline's pooled buffers see chunk after chunk of one
 // geometry) runs the whole kernel sequence with the previous call's plan and buffer sizes and only then looks at the
 // numbers the checked path waits for twice (distinct values per chunk, bins per chunk, events): no host round trip
-// inside the sequence, one at its end. Every kernel stays inside its buffers whatever the data (compact ids are
-// clamped, events beyond the pool and chunks beyond the bin buffer are skipped); when a check fails the result is
-// discarded and the checked path runs.
-int run_speculative(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, uint32_t* h_nbiomes,
-                    uint64_t* h_totals, cudaStream_t s) {
-    (void)f;
+// inside the sequence. Every kernel stays inside its buffers whatever the data (compact ids are clamped, events beyond
+// the pool and chunks beyond the bin buffer are skipped). The look happens in settle(): right away for the blocking
+// entry points, at the first query of the result for shf_run_device_async; when a check fails the result is discarded
+// and the checked path runs on the same input.
+int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, uint32_t* h_nbiomes,
+                        uint64_t* h_totals, cudaStream_t s) {
     const uint32_t n_chunks = g.n_chunks;
     const int K = (int)g.K;
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
     SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
-    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks), n_chunks);
+    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks, f->sm_count), n_chunks);
     if (vec8)
         shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
     else
@@ -416,7 +454,7 @@ int run_speculative(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev,
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
     SHF_CUDA(b->mark(1, s));
-    int st = prepare_common(b, g, in_dev, vec8, s);
+    int st = prepare_common(f, b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
     st = dispatch_chain(K, b, g, s, 0);
     if (st != SHF_OK) return st;
@@ -435,19 +473,48 @@ int run_speculative(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev,
     SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
     SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, s));
     tls_d2h += (size_t)n_chunks * 12 + 8;
-    SHF_CUDA(cudaStreamSynchronize(s));
-    // ---- the checks the other path makes before it launches ----
+    return SHF_OK;
+}
+
+// page-locked scratch of a call: distinct values per chunk (u32) and bins per chunk + event count (u64)
+void small_host_views(shf_buffer* b, uint32_t n_chunks, uint32_t** h_nbiomes, uint64_t** h_totals) {
+    *h_nbiomes = b->h_small.as<uint32_t>();
+    *h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
+}
+
+int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s);
+
+// Completes a call enqueued by enqueue_speculative: waits for it, makes the checks the other path makes before it
+// launches and publishes the result -- or runs the checked path when the previous call's plan or buffer sizes did not
+// fit this input. SHF_OK without work when nothing is pending.
+int settle(shf_buffer* b) {
+    if (!b->deferred.active) return SHF_OK;
+    shf_buffer::Deferred d = b->deferred;
+    b->deferred.active = false;
+    SHF_CUDA(cudaEventSynchronize(b->done_ev));
+    const Geo& g = d.g;
+    const uint32_t n_chunks = g.n_chunks;
+    uint32_t* h_nbiomes;
+    uint64_t* h_totals;
+    small_host_views(b, n_chunks, &h_nbiomes, &h_totals);
     uint32_t bmax = 0;
     for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
     const uint32_t need_k = bmax <= 32u ? 1u : bmax <= 64u ? 2u : bmax <= 128u ? 4u : 8u;
-    if (bmax > 256u || need_k != g.K) return kSpecMiss;               // another plan (or the wide path) is due
-    if (h_totals[n_chunks] > b->evpool.cap / 8) return kSpecMiss;      // event pool too small
+    bool hit = bmax <= 256u && need_k == g.K;                              // else another plan (or the wide path) is due
+    hit = hit && h_totals[n_chunks] <= b->evpool.cap / 8;                  // event pool large enough
     uint64_t total = 0;
-    for (uint32_t i = 0; i < n_chunks; i++) {
-        if (h_totals[i] > 0xFFFFFFFFull) return kSpecMiss;             // the checked path reports the overflow
+    for (uint32_t i = 0; i < n_chunks && hit; i++) {
+        hit = h_totals[i] <= 0xFFFFFFFFull;                                // (the checked path reports the overflow)
         total += h_totals[i];
     }
-    if (total > b->bins.cap / sizeof(shf_bin)) return kSpecMiss;       // bin buffer too small
+    hit = hit && total <= b->bins.cap / sizeof(shf_bin);                   // bin buffer large enough
+    if (!hit) {
+        b->last_valid = false;
+        b->spec_misses++;
+        const int st = run_checked(&d.filt, b, g, d.in_dev, d.vec8, d.stream);
+        if (st == SHF_OK) SHF_CUDA(cudaEventRecord(b->done_ev, d.stream));
+        return st;
+    }
     b->chunk_base.assign(n_chunks + 1u, 0ull);
     for (uint32_t i = 0; i < n_chunks; i++) b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
     b->plan_biomes = bmax;
@@ -455,8 +522,9 @@ int run_speculative(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev,
 }
 
 // Run the whole kernel sequence. `in_dev` views the halo-extended region of every chunk in device memory.
+// deferred: return as soon as everything is enqueued when the call can run ahead (settle() completes it later).
 int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t in_chunk_stride, uint32_t in_row_stride,
-                  uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s) {
+                  uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s, bool deferred = false) {
     Geo g{};
     g.W = W;
     g.H = H;
@@ -473,34 +541,67 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     if (n_chunks > 65535u) return fail(SHF_ERR_UNSUPPORTED, "n_chunks <= 65535", "too many chunks in one batch");
     if (g.PH >= 65535u) return fail(SHF_ERR_UNSUPPORTED, "H + 2*radius < 65535", "map too tall for 16-bit row keys");
 
+    // A call still waiting for its checks is simply dropped: this call replaces its result. Work of an earlier call may
+    // still be running on another stream (the device entry points leave their last kernels in flight on the caller's
+    // stream): this call's stream waits for it before it touches the buffer's scratch.
+    b->deferred.active = false;
+    b->has_result = false;
+    if (!b->done_ev) SHF_CUDA(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
+    if (b->done_recorded && b->done_stream != s) SHF_CUDA(cudaStreamWaitEvent(s, b->done_ev, 0));
+    if ((size_t)n_chunks * 16 + 64 > b->h_small.cap && b->done_recorded)
+        SHF_CUDA(cudaEventSynchronize(b->done_ev));  // (a copy into the old page-locked block may be in flight)
+
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
     SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 64));
-    uint32_t* h_nbiomes = b->h_small.as<uint32_t>();
-    uint64_t* h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
+    uint32_t* h_nbiomes;
+    uint64_t* h_totals;
+    small_host_views(b, n_chunks, &h_nbiomes, &h_totals);
 
     // 16-byte loads when the halo view allows it
     const bool vec8 = (reinterpret_cast<uintptr_t>(in_dev) % 16u == 0u) && (in_row_stride % 8u == 0u) && (in_chunk_stride % 8u == 0u);
 
     // ---- same shape as the last call on this buffer: run with its plan, check afterwards ----
-    // (small calls only: a batch of hundreds of chunks does not notice two round trips, but would pay the check at the
-    // end of the call as a bubble before the next one)
+    int st;
     if (b->last_valid && b->last_g.W == W && b->last_g.H == H && b->last_g.r == r && b->last_g.n_chunks == n_chunks &&
-        (uint64_t)n_chunks * W * H <= (16ull << 20) && !getenv("SHF_NO_SPECULATION")) {
+        !f->dbg.no_speculation) {
         Geo gs = b->last_g;
         gs.in_row_stride = in_row_stride;
         gs.in_chunk_stride = in_chunk_stride;
-        const int st = run_speculative(f, b, gs, in_dev, vec8, h_nbiomes, h_totals, s);
-        if (st != kSpecMiss) return st;
-        b->last_valid = false;
+        st = enqueue_speculative(f, b, gs, in_dev, vec8, h_nbiomes, h_totals, s);
+        if (st != SHF_OK) return st;
+        SHF_CUDA(cudaEventRecord(b->done_ev, s));
+        b->done_recorded = true;
+        b->done_stream = s;
+        b->deferred.active = true;
+        b->deferred.filt = *f;
+        b->deferred.g = gs;
+        b->deferred.in_dev = in_dev;
+        b->deferred.vec8 = vec8;
+        b->deferred.stream = s;
+        return deferred ? SHF_OK : settle(b);
     }
+    st = run_checked(f, b, g, in_dev, vec8, s);
+    if (st != SHF_OK) return st;
+    SHF_CUDA(cudaEventRecord(b->done_ev, s));
+    b->done_recorded = true;
+    b->done_stream = s;
+    return SHF_OK;
+}
 
+// The checked path: two host round trips (distinct values per chunk -> plan; bins per chunk -> bin buffer).
+int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
+    const uint32_t n_chunks = g.n_chunks, W = g.W, H = g.H, r = g.r;
+    (void)r;
+    uint32_t* h_nbiomes;
+    uint64_t* h_totals;
+    small_host_views(b, n_chunks, &h_nbiomes, &h_totals);
     // ---- dictionary ----
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
     SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
-    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks), n_chunks);
+    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks, f->sm_count), n_chunks);
     if (vec8)
         shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
     else
@@ -523,7 +624,8 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     // The event-list path covers up to 256 distinct values and 2r+1 <= 511 (8-bit vertical window counts up to 255,
     // 16-bit ones beyond) as long as one row's ring fits shared memory; everything else takes the wide path.
     g.FW = g.span <= 255u ? 8u : 16u;
-    bool generic = bmax > 256u || g.span > 511u;
+    // (the event records pack pixel columns into 16 bits: wider maps take the wide path, which does not)
+    bool generic = bmax > 256u || g.span > 511u || g.PW > 65535u;
     if (!generic) {
         g.Bpad = 32u * K;
         // emit kernel plan: rows per CTA (<= 16), producer warps, ring depth. A batch of 16 columns is produced in
@@ -557,7 +659,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         // small calls: 8 rows per CTA when 16 would leave more than half of the SMs idle (a single 512x512 chunk has 32
         // tiles of 16 rows: emit 0.054 -> 0.046 ms; a 2048x2048 chunk with its 128 tiles is better off with 16)
         // (8, not fewer: vscan dumps a base vector per tile and its fast variant wants multiples of 8)
-        if (const char* e = getenv("SHF_DEBUG_TY")) ty = std::max(1u, std::min(ty, (uint32_t)atoi(e)));  // measurements only
+        if (f->dbg.debug_ty) ty = std::max(1u, std::min(ty, f->dbg.debug_ty));  // measurements only
         else if (ty > 8u && (uint64_t)n_chunks * ((H + ty - 1u) / ty) * 2u <= (uint64_t)f->sm_count) ty = 8u;
         if (smem_of(ty) > f->smem_optin) {
             generic = true;
@@ -571,13 +673,13 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         // tiles of 8 rows) is split into column segments, each sliding over the 2r columns before its first pixel
         g.cseg = 1u;
         g.cseg_px = W;
-        if (!generic && !getenv("SHF_NO_CSEG")) {
+        if (!generic && !f->dbg.no_cseg) {
             const uint64_t ctas = (uint64_t)n_chunks * g.T;
             // (measured: 2 segments for 64..147 CTAs, 4 below; nothing to gain when one CTA fills an SM's shared memory)
             uint32_t want = 2u * smem_of(ty) > f->smem_optin ? 1u
                             : ctas * 2u <= (uint64_t)f->sm_count ? 4u
                             : ctas < (uint64_t)f->sm_count ? 2u : 1u;
-            if (const char* e = getenv("SHF_DEBUG_CSEG")) want = std::max(1u, (uint32_t)atoi(e));  // measurements only
+            if (f->dbg.debug_cseg) want = f->dbg.debug_cseg;  // measurements only
             want = std::min(want, 8u);
             while (want > 1u) {
                 const uint32_t px = ((W + want - 1u) / want + 15u) & ~15u;
@@ -594,9 +696,9 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         g.vseg = 1u;
         g.vseg_rows = 0u;
         const uint64_t vwarps = (uint64_t)n_chunks * ((g.PW + 31u) / 32u);
-        if (!generic && vwarps < 2ull * (uint64_t)f->sm_count && !getenv("SHF_NO_VSEG")) {
+        if (!generic && vwarps < 2ull * (uint64_t)f->sm_count && !f->dbg.no_vseg) {
             uint32_t S = 8u;
-            if (const char* e = getenv("SHF_DEBUG_VSEG")) S = std::max(1u, (uint32_t)atoi(e));  // measurements only
+            if (f->dbg.debug_vseg) S = f->dbg.debug_vseg;  // measurements only
             while (S > 1u) {
                 const uint32_t L = (((H - 1u) + S - 1u) / S + 31u) & ~31u;   // output rows per segment
                 if (L >= std::max(64u, g.span / 2u) && 1u + (S - 1u) * L < H && vwarps * S <= 4ull * (uint64_t)f->sm_count) {
@@ -625,7 +727,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         SHF_CUDA(b->rowinfo.ensure((size_t)n_chunks * H * 8));
         SHF_CUDA(b->evpool.ensure((size_t)n_chunks * H * 32u * (K + 1) * 8));
     }
-    int st = prepare_common(b, g, in_dev, vec8, s);
+    int st = prepare_common(f, b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
 
     // ---- vertical scan + bins per row ----
@@ -644,8 +746,8 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     return publish(b, g);
 }
 
+// (the calling entry point holds a DeviceGuard on f->device)
 int bind_device(const shf_filter* f, shf_buffer* b) {
-    SHF_CUDA(cudaSetDevice(f->device));
     if (b->device != f->device) {
         if (b->device >= 0) {
             cudaSetDevice(b->device);
@@ -679,6 +781,7 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
         return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
     int st = validate(map_size, nn, radius);
     if (st != SHF_OK) return st;
+    DeviceGuard guard(f->device);
     st = bind_device(f, b);
     if (st != SHF_OK) return st;
     const uint32_t W = map_size[0], H = map_size[1], r = radius;
@@ -686,6 +789,8 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
     const size_t sx = (size_t)W * (nn[0] / 2u), sy = (size_t)H * (nn[1] / 2u);
     const size_t S = total[0];
     if (S < sx + W + r) return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.x >= start + W + r", "row stride too small");
+    if (total[1] < sy + H + r)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.y >= start + H + r", "the bottom halo lies outside the merged map");
     b->has_result = false;
     cudaStream_t s = b->stream;
     const size_t cells = (size_t)PH * P;
@@ -719,6 +824,7 @@ int run_multi(shf_filter* f, const uint16_t* const* maps, shf_buffer* const* buf
     shf_buffer* lead = buffers[0];
     int st = run_host(f, maps, n_calls, map_size, nn, total, lead, radius, false);
     if (st != SHF_OK) return st;
+    DeviceGuard guard(f->device);
     cudaStream_t s = lead->stream;
     const size_t per = (size_t)map_size[0] * map_size[1] + 1u;
     const std::vector<uint64_t> base = lead->chunk_base;
@@ -795,6 +901,13 @@ int run_neighbours(shf_filter* f, const uint16_t* const* chunk_maps, uint32_t n_
     if (n_chunks == 0u) return fail(SHF_ERR_INVALID_ARGUMENT, "n_chunks > 0", "empty batch");
     int st = validate(map_size, nn, radius);
     if (st != SHF_OK) return st;
+    // the right / bottom halo must lie inside the neighbourhood as well (validate() only looks at the left / top margin;
+    // an even neighbour count or a large radius would leave halo cells without a source map)
+    if ((uint64_t)map_size[0] * (nn[0] / 2u) + map_size[0] + radius > (uint64_t)nn[0] * map_size[0] ||
+        (uint64_t)map_size[1] * (nn[1] / 2u) + map_size[1] + radius > (uint64_t)nn[1] * map_size[1])
+        return fail(SHF_ERR_INVALID_ARGUMENT, "start + MapSize + radius <= NearestNeighbour * MapSize",
+                    "the right / bottom halo lies outside the chunk neighbourhood");
+    DeviceGuard guard(f->device);
     st = bind_device(f, b);
     if (st != SHF_OK) return st;
     b->has_result = false;
@@ -805,6 +918,13 @@ int run_neighbours(shf_filter* f, const uint16_t* const* chunk_maps, uint32_t n_
     st = run_on_device(f, b, b->din.as<uint16_t>(), (size_t)PH * P, P, n_chunks, map_size[0], map_size[1], radius, s);
     if (st != SHF_OK) return st;
     return to_host ? result_to_host(b, s) : SHF_OK;
+}
+
+// the const accessors complete a call that is still waiting for its checks
+int settle_const(const shf_buffer* b) {
+    if (!b->deferred.active) return SHF_OK;
+    DeviceGuard guard(b->device);
+    return settle(const_cast<shf_buffer*>(b));
 }
 
 }  // namespace
@@ -833,6 +953,16 @@ int shf_filter_create(shf_filter** out, int device) {
         return fail(SHF_ERR_CUDA, "cudaDeviceGetAttribute", cudaGetErrorString(e));
     }
     f->smem_optin = (size_t)v;
+    auto env_u32 = [](const char* name) {
+        const char* e = getenv(name);
+        return e ? (uint32_t)std::max(1, atoi(e)) : 0u;
+    };
+    f->dbg.no_speculation = getenv("SHF_NO_SPECULATION") != nullptr;
+    f->dbg.no_cseg = getenv("SHF_NO_CSEG") != nullptr;
+    f->dbg.no_vseg = getenv("SHF_NO_VSEG") != nullptr;
+    f->dbg.debug_ty = env_u32("SHF_DEBUG_TY");
+    f->dbg.debug_cseg = env_u32("SHF_DEBUG_CSEG");
+    f->dbg.debug_vseg = env_u32("SHF_DEBUG_VSEG");
     *out = f;
     return SHF_OK;
 }
@@ -865,6 +995,7 @@ void shf_buffer_destroy(shf_buffer* buffer) {
 
 int shf_buffer_read(const shf_buffer* b, const shf_bin** bins, const uint32_t** offsets) {
     if (!b || !bins || !offsets) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     if (!b->has_result || !b->on_host) {
         *bins = nullptr;
         *offsets = nullptr;
@@ -877,6 +1008,7 @@ int shf_buffer_read(const shf_buffer* b, const shf_bin** bins, const uint32_t** 
 
 int shf_buffer_size(const shf_buffer* b, size_t* n_bins, size_t* n_offsets) {
     if (!b || !n_bins || !n_offsets) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     *n_bins = b->has_result ? b->n_bins : 0;
     *n_offsets = b->has_result ? b->n_offsets : 0;
     return SHF_OK;
@@ -896,22 +1028,45 @@ int shf_run_batch(shf_filter* filter, const uint16_t* const* samplemaps, uint32_
     return run_host(filter, samplemaps, n_chunks, map_size, nn, total, buffer, radius);
 }
 
-int shf_run_device(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_stride, uint32_t n_chunks,
-                   const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], shf_buffer* b,
-                   uint32_t radius, void* stream) {
+static int run_device_entry(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_stride, uint32_t n_chunks,
+                            const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], shf_buffer* b,
+                            uint32_t radius, void* stream, bool deferred) {
     if (!f || !b || !maps_dev || !map_size || !nn || !total)
         return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
     int st = validate(map_size, nn, radius);
     if (st != SHF_OK) return st;
+    DeviceGuard guard(f->device);
     st = bind_device(f, b);
     if (st != SHF_OK) return st;
     const uint32_t W = map_size[0], H = map_size[1];
     const size_t sx = (size_t)W * (nn[0] / 2u), sy = (size_t)H * (nn[1] / 2u);
     const size_t S = total[0];
     if (S < sx + W + radius) return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.x >= start + W + r", "row stride too small");
+    if (total[1] < sy + H + radius)
+        return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.y >= start + H + r", "the bottom halo lies outside the merged map");
     b->has_result = false;
     const uint16_t* view = maps_dev + (sy - radius) * S + (sx - radius);
-    return run_on_device(f, b, view, chunk_stride, (uint32_t)S, n_chunks, W, H, radius, static_cast<cudaStream_t>(stream));
+    return run_on_device(f, b, view, chunk_stride, (uint32_t)S, n_chunks, W, H, radius, static_cast<cudaStream_t>(stream),
+                         deferred);
+}
+
+int shf_run_device(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_stride, uint32_t n_chunks,
+                   const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], shf_buffer* b,
+                   uint32_t radius, void* stream) {
+    return run_device_entry(f, maps_dev, chunk_stride, n_chunks, map_size, nn, total, b, radius, stream, false);
+}
+
+int shf_run_device_async(shf_filter* f, const uint16_t* maps_dev, uint64_t chunk_stride, uint32_t n_chunks,
+                         const uint32_t map_size[2], const uint32_t nn[2], const uint32_t total[2], shf_buffer* b,
+                         uint32_t radius, void* stream) {
+    return run_device_entry(f, maps_dev, chunk_stride, n_chunks, map_size, nn, total, b, radius, stream, true);
+}
+
+int shf_buffer_wait(shf_buffer* b, uint64_t* repeated_calls) {
+    if (!b) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer != NULL", "null argument");
+    const int st = settle_const(b);
+    if (repeated_calls) *repeated_calls = b->spec_misses;
+    return st;
 }
 
 int shf_run_multi(shf_filter* filter, const uint16_t* const* samplemaps, shf_buffer* const* buffers, uint32_t n_calls,
@@ -932,6 +1087,7 @@ int shf_run_neighbours_device(shf_filter* filter, const uint16_t* const* neighbo
 
 int shf_buffer_read_device(const shf_buffer* b, const shf_bin** bins_dev, const uint32_t** offsets_dev) {
     if (!b || !bins_dev || !offsets_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     *bins_dev = b->has_result && b->dev_valid ? b->bins.as<shf_bin>() : nullptr;
     *offsets_dev = b->has_result && b->dev_valid ? b->hso.as<uint32_t>() : nullptr;
     return SHF_OK;
@@ -939,6 +1095,7 @@ int shf_buffer_read_device(const shf_buffer* b, const shf_bin** bins_dev, const 
 
 int shf_buffer_chunk_base(const shf_buffer* b, const uint64_t** chunk_base, uint32_t* n_chunks) {
     if (!b || !chunk_base || !n_chunks) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     *chunk_base = b->has_result ? b->chunk_base.data() : nullptr;
     *n_chunks = b->has_result ? b->n_chunks : 0u;
     return SHF_OK;
@@ -954,10 +1111,11 @@ int shf_heightfield_create(shf_heightfield** out, shf_filter* f, const shf_biome
     const size_t smem = 1024 + (size_t)gradient2d_size * 8 + (size_t)n_table * sizeof(shf_biome_property);
     if (smem > f->smem_optin)
         return fail(SHF_ERR_UNSUPPORTED, "tables fit shared memory", "biome / gradient tables too large for one CTA");
-    SHF_CUDA(cudaSetDevice(f->device));
+    DeviceGuard guard(f->device);
     shf_heightfield* h = new (std::nothrow) shf_heightfield();
     if (!h) return fail(SHF_ERR_INVALID_ARGUMENT, "new shf_heightfield", "out of host memory");
     h->device = f->device;
+    h->sm_count = f->sm_count;
     h->smem_optin = f->smem_optin;
     h->n_table = n_table;
     h->grad_size = gradient2d_size;
@@ -991,12 +1149,13 @@ void shf_heightfield_destroy(shf_heightfield* h) {
 int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk, uint32_t n_chunks, const float* offsets_xy,
                         float* height_dev, void* stream) {
     if (!h || !b || !offsets_xy || !height_dev) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     if (!b->has_result || !b->dev_valid)
         return fail(SHF_ERR_INVALID_ARGUMENT, "buffer holds a device result", "run the filter on this buffer first");
     if (b->device != h->device) return fail(SHF_ERR_INVALID_ARGUMENT, "same device", "histogram and generator live on different devices");
     if (n_chunks == 0u || first_chunk > b->n_chunks || n_chunks > b->n_chunks - first_chunk || n_chunks > 65535u)
         return fail(SHF_ERR_INVALID_ARGUMENT, "chunk range inside the last result", "no such chunks");
-    SHF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SHF_CUDA(b->hf_offsets.ensure((size_t)n_chunks * 8));
     SHF_CUDA(cudaMemcpyAsync(b->hf_offsets.p, offsets_xy, (size_t)n_chunks * 8, cudaMemcpyHostToDevice, s));
@@ -1011,7 +1170,7 @@ int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk,
     const size_t smem = 1024 + (size_t)h->grad_size * 8 + (size_t)h->n_table * sizeof(shf_biome_property);
     SHF_CUDA(cudaFuncSetAttribute(shf::heightfield_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t npx = g.W * g.H;
-    const uint32_t gx = std::max(1u, std::min((npx + 255u) / 256u, 148u * 8u));
+    const uint32_t gx = std::max(1u, std::min((npx + 255u) / 256u, (uint32_t)h->sm_count * 8u));
     shf::heightfield_kernel<<<dim3(gx, n_chunks), 256, smem, s>>>(
         g, b->bins.as<uint2>(), b->hso.as<uint32_t>(), b->chunkbase.as<uint64_t>(), first_chunk,
         h->table.as<shf_biome_property>(), h->perm.as<unsigned char>(), h->grad.as<float>(), b->hf_offsets.as<float2>(),
@@ -1035,6 +1194,7 @@ void shf_set_profiling(int enabled) { g_profiling = enabled ? 1 : 0; }
 
 int shf_buffer_phase_history(const shf_buffer* b, uint32_t back, float* ms, uint32_t n) {
     if (!b || !ms) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     if (!b->ev_valid) return fail(SHF_ERR_INVALID_ARGUMENT, "profiling enabled", "no phase events recorded for the last call");
     if (back >= (uint32_t)kEvRing || back >= b->ev_calls)
         return fail(SHF_ERR_INVALID_ARGUMENT, "back < profiled calls kept", "no phase events kept that far back");
@@ -1051,6 +1211,7 @@ int shf_buffer_phase_ms(const shf_buffer* b, float* ms, uint32_t n) { return shf
 int shf_buffer_last_plan(const shf_buffer* b, uint32_t* k_sets, uint32_t* rows_per_cta, uint32_t* n_biomes,
                          uint32_t* smem_bytes) {
     if (!b) return fail(SHF_ERR_INVALID_ARGUMENT, "buffer != NULL", "null argument");
+    if (const int st = settle_const(b)) return st;
     if (k_sets) *k_sets = b->plan_k;
     if (rows_per_cta) *rows_per_cta = b->plan_ty;
     if (n_biomes) *n_biomes = b->plan_biomes;

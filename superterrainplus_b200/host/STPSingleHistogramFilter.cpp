@@ -93,6 +93,12 @@ STPSingleHistogram STPFilterBuffer::readDeviceHistogram() const {
 	return STPSingleHistogram { reinterpret_cast<const STPSingleHistogram::STPBin*>(bin), offset };
 }
 
+std::uint64_t STPFilterBuffer::wait() {
+	uint64_t repeated;
+	check(shf_buffer_wait(this->Memory, &repeated));
+	return repeated;
+}
+
 std::uint64_t STPFilterBuffer::chunkOffset(const unsigned int chunk) const {
 	const uint64_t* base;
 	uint32_t count;
@@ -155,5 +161,13 @@ void STPSingleHistogramFilter::filterDevice(const STPSample_t* const samplemap_d
 	const unsigned int radius, void* const stream) {
 	const STPGeometry geo(nn_info);
 	check(shf_run_device(this->Filter, samplemap_device, chunk_stride, chunk_count, geo.MapSize, geo.Neighbour, geo.Total,
+		filter_buffer.Memory, radius, stream));
+}
+
+void STPSingleHistogramFilter::filterDeviceAsync(const STPSample_t* const samplemap_device, const std::uint64_t chunk_stride,
+	const unsigned int chunk_count, const STPNearestNeighbourInformation& nn_info, STPFilterBuffer& filter_buffer,
+	const unsigned int radius, void* const stream) {
+	const STPGeometry geo(nn_info);
+	check(shf_run_device_async(this->Filter, samplemap_device, chunk_stride, chunk_count, geo.MapSize, geo.Neighbour, geo.Total,
 		filter_buffer.Memory, radius, stream));
 }

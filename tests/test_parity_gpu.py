@@ -231,10 +231,12 @@ def test_vscan_row_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segmen
             monkeypatch.delenv("SHF_DEBUG_VSEG", raising=False)
         else:
             monkeypatch.setenv("SHF_DEBUG_VSEG", setting)
+        local = shf.STPSingleHistogramFilter()   # the measurement toggles are read when a filter is created
         buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
-        got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+        got = split_result(local(m, nn_info(shf, w, h, nn), buf, r))
         assert_same(got, want, f"{w}x{h} r={r} B={biomes} {kind} segments={setting}")
         buf.close()
+        local.close()
 
 
 @pytest.mark.parametrize("w,h,r,biomes,kind,segments", [
@@ -257,10 +259,12 @@ def test_emit_column_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segm
             monkeypatch.delenv("SHF_DEBUG_CSEG", raising=False)
         else:
             monkeypatch.setenv("SHF_DEBUG_CSEG", setting)
+        local = shf.STPSingleHistogramFilter()   # the measurement toggles are read when a filter is created
         buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
-        got = split_result(filt(m, nn_info(shf, w, h, nn), buf, r))
+        got = split_result(local(m, nn_info(shf, w, h, nn), buf, r))
         assert_same(got, want, f"{w}x{h} r={r} B={biomes} {kind} column segments={setting}")
         buf.close()
+        local.close()
 
 
 def split_neighbours(m, w, h, nn):
@@ -386,9 +390,18 @@ def test_device_resident(shf, filt, oracle_mod):
     buf.close()
 
 
-@pytest.mark.parametrize("name,dist", [("C1", "uniform"), ("C1", "blocky"), ("C2", "blocky")])
+def cpu_filter(oracle_mod, m, wl):
+    """The reference's own compiled filter when it travelled to this box (oracle/_ref), else the C restatement."""
+    if oracle_mod.have_reference():
+        return oracle_mod.run_reference(m, wl.map_size, wl.nn, wl.radius)
+    return oracle_mod.run_port(m, wl.map_size, wl.nn, wl.radius)
+
+
+@pytest.mark.parametrize("name,dist", [("C1", "uniform"), ("C1", "blocky"), ("C2", "uniform"), ("C2", "blocky"),
+                                       ("C4", "blocky"), ("C4", "uniform")])
 def test_baseline_configs_vs_oracle(shf, filt, oracle_mod, name, dist):
-    """BASELINE.json configs small enough for the oracle to finish in seconds: full comparison."""
+    """BASELINE.json's single-neighbourhood configs at their full sizes (512x512 r=32 B=8, 1024x1024 r=64 B=32, one
+    2048x2048 chunk r=64 B=32), dense and clustered ids: every pixel's items, offsets and weight bits."""
     import dataclasses
     from superterrainplus_b200 import workloads
 
@@ -396,8 +409,160 @@ def test_baseline_configs_vs_oracle(shf, filt, oracle_mod, name, dist):
     m = workloads.make_map_np(wl, 0)
     buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
     got = split_result(filt(m, shf.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total), buf, wl.radius))
-    assert_same(got, oracle_mod.run_port(m, wl.map_size, wl.nn, wl.radius), f"{name} {dist}")
+    assert_same(got, cpu_filter(oracle_mod, m, wl), f"{name} {dist}")
     buf.close()
+
+
+@pytest.mark.parametrize("dist", ["uniform", "blocky"])
+def test_c3_full_batch_256_chunks(shf, filt, oracle_mod, dist):
+    """The configuration every headline number is quoted on, at its full size: 256 neighbourhoods of 512x512, r=64, 64
+    biomes, device-resident (the bench's own call sequence: one checked call, then shf_run_device_async on OTHER chunk
+    ids with the first call's plan, completed by wait()). Every chunk through size-independent properties evaluated on
+    the device (offsets start at 0, grow by 1..64 per pixel and close on the chunk's bin total; every weight is
+    count * 1/(2r+1)^2 bit for bit with count >= 1; counts of a pixel sum to (2r+1)^2; items distinct within a pixel);
+    four chunks against the reference CPU filter in full."""
+    import dataclasses
+    import torch
+    from superterrainplus_b200 import workloads
+
+    wl = dataclasses.replace(workloads.CONFIGS["C3"], dist=dist)
+    n = wl.chunks
+    w, h = wl.map_size
+    tw, th = wl.total
+    dev = torch.device("cuda", 0)
+    info = shf.STPNearestNeighbourInformation(wl.map_size, wl.nn, wl.total)
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    stream = torch.cuda.current_stream().cuda_stream
+    warm = workloads.make_maps_torch(wl, 1000, n, dev)
+    filt.runDevice(warm.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
+    torch.cuda.synchronize()
+    del warm
+    maps = workloads.make_maps_torch(wl, 0, n, dev)
+    filt.runDeviceAsync(maps.data_ptr(), th * tw, n, info, buf, wl.radius, stream)
+    buf.wait()
+    torch.cuda.synchronize()
+    bins_p, offs_p = buf.readDevice()
+    base = buf.chunkBase()
+    n_bins, n_offs = buf.size()
+    per = w * h + 1
+    assert n_offs == n * per and n_bins == int(base[-1]) and len(base) == n + 1
+    total = (2 * wl.radius + 1) ** 2
+    inv = torch.tensor(1.0, dtype=torch.float32, device=dev) / torch.tensor(float(total), dtype=torch.float32, device=dev)
+    from superterrainplus_b200.api import DeviceArrayView
+    for i in range(n):
+        lo, hi = int(base[i]), int(base[i + 1])
+        raw = torch.as_tensor(DeviceArrayView(bins_p + lo * 8, 2 * (hi - lo)), device=dev).view(hi - lo, 2)
+        offs = torch.as_tensor(DeviceArrayView(offs_p + i * per * 4, per), device=dev)
+        offs = offs.to(torch.int64) & 0xFFFFFFFF
+        assert int(offs[0]) == 0 and int(offs[-1]) == hi - lo, f"chunk {i}: offsets do not span the chunk's bins"
+        nb = offs[1:] - offs[:-1]
+        assert int(nb.min()) >= 1 and int(nb.max()) <= wl.biomes, f"chunk {i}: bins per pixel out of range"
+        items = raw[:, 0].to(torch.int64) & 0xFFFF
+        assert int((raw[:, 0].to(torch.int64) & 0xFFFF0000).abs().max()) == 0, f"chunk {i}: padding bytes not zero"
+        weights = raw[:, 1].view(torch.float32)
+        counts = torch.round(weights.to(torch.float64) * total).to(torch.int64)
+        assert int(counts.min()) >= 1
+        assert torch.equal((counts.to(torch.float32) * inv).view(torch.int32), raw[:, 1]), f"chunk {i}: weight bits"
+        csum = torch.cumsum(counts, 0)
+        ends = csum[offs[1:] - 1]
+        sums = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
+        assert bool((sums == total).all()), f"chunk {i}: window counts do not sum to (2r+1)^2"
+        px = torch.repeat_interleave(torch.arange(w * h, device=dev, dtype=torch.int64), nb)
+        key = torch.sort(px * 65536 + items).values
+        assert bool((key[1:] != key[:-1]).all()), f"chunk {i}: an item appears twice in one pixel"
+        if i in (0, 85, 170, 255):
+            got = (items.to(torch.int32).cpu().numpy().astype(np.uint16), weights.cpu().numpy().copy(),
+                   offs.cpu().numpy().astype(np.uint32))
+            assert_same(got, cpu_filter(oracle_mod, maps[i].cpu().numpy(), wl), f"C3 {dist} chunk {i}")
+        del raw, offs, items, weights, counts, csum, ends, sums, px, key
+    buf.close()
+
+
+def test_async_call_with_unfitting_plan_is_repeated(shf, filt, oracle_mod):
+    """shf_run_device_async runs with the previous call's plan; when the new maps need another one (more distinct values
+    -> more register sets, more bins than the buffer holds) the first query repeats the call on the checked path."""
+    import torch
+
+    w, h, r = 96, 80, 16
+    rng = np.random.default_rng(99)
+    info = nn_info(shf, w, h)
+    small = [random_map(rng, w, h, 5, "blocky") for _ in range(3)]
+    big = [random_map(rng, w, h, 150, "iid") for _ in range(3)]
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    dev = torch.device("cuda", 0)
+    d_small = torch.from_numpy(np.stack(small).view(np.int16)).to(dev)
+    d_big = torch.from_numpy(np.stack(big).view(np.int16)).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    filt.runDevice(d_small.data_ptr(), 9 * w * h, 3, info, buf, r, stream)
+    before = buf.wait()
+    filt.runDeviceAsync(d_small.data_ptr(), 9 * w * h, 3, info, buf, r, stream)   # abandoned: replaced by the next call
+    filt.runDeviceAsync(d_big.data_ptr(), 9 * w * h, 3, info, buf, r, stream)
+    assert buf.wait() == before + 1
+    torch.cuda.synchronize()
+    bins_p, offs_p = buf.readDevice()
+    base = buf.chunkBase()
+    n_bins, n_offs = buf.size()
+    import ctypes
+    cudart = ctypes.CDLL("libcudart.so.12")
+    bins = np.zeros(n_bins, dtype=shf.BIN_DTYPE)
+    offs = np.zeros(n_offs, dtype=np.uint32)
+    assert cudart.cudaMemcpy(ctypes.c_void_p(bins.ctypes.data), ctypes.c_void_p(bins_p), ctypes.c_size_t(bins.nbytes), 2) == 0
+    assert cudart.cudaMemcpy(ctypes.c_void_p(offs.ctypes.data), ctypes.c_void_p(offs_p), ctypes.c_size_t(offs.nbytes), 2) == 0
+    per = w * h + 1
+    for i in range(3):
+        got = (bins["Item"][base[i]:base[i + 1]].copy(), bins["Weight"][base[i]:base[i + 1]].copy(), offs[i * per:(i + 1) * per].copy())
+        assert_same(got, oracle_mod.run_port(big[i], (w, h), (3, 3), r), f"repeated async chunk {i}")
+    # and once the plan fits, nothing is repeated
+    filt.runDeviceAsync(d_big.data_ptr(), 9 * w * h, 3, info, buf, r, stream)
+    assert buf.wait() == before + 1
+    buf.close()
+
+
+def test_wide_maps_leave_the_16_bit_event_records(shf, filt, oracle_mod):
+    """W + 2r >= 65536: pixel columns no longer fit the event records' 16 bits; such maps take the wide path."""
+    w, h, r = 70000, 4, 2
+    rng = np.random.default_rng(5)
+    m = random_map(rng, w, h, 9, "rare")
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    got = split_result(filt(m, nn_info(shf, w, h), buf, r))
+    assert buf.lastPlan()["k_sets"] == 0
+    assert_same(got, oracle_mod.run_port(m, (w, h), (3, 3), r), "W=70000")
+    buf.close()
+
+
+def test_halo_outside_the_neighbourhood_is_rejected(shf, filt):
+    """An even neighbour count leaves the right / bottom halo without a source (validate() only guards left / top)."""
+    w, h, r = 16, 16, 4
+    buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+    maps = [np.zeros((h, w), dtype=np.uint16) for _ in range(4)]
+    with pytest.raises(ValueError):
+        filt.runNeighbours(maps, shf.STPNearestNeighbourInformation((w, h), (2, 2), (2 * w, 2 * h)), buf, r)
+    merged = np.zeros((2 * h, 2 * w + 8), dtype=np.uint16)   # wide enough in x, too short in y
+    with pytest.raises(ValueError):
+        filt(merged, shf.STPNearestNeighbourInformation((w, h), (2, 2), (2 * w + 8, 2 * h)), buf, r)
+    buf.close()
+
+
+def test_calls_leave_the_current_device_alone(shf, filt):
+    """The reference's operator() never touches CUDA device state; the library restores the caller's device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    torch.cuda.set_device(1)
+    try:
+        buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+        f0 = shf.STPSingleHistogramFilter(0)
+        f0(GOLDEN_TEXTURE, nn_info(shf, 4, 4), buf, 2)
+        assert torch.cuda.current_device() == 1
+        import ctypes
+        dev = ctypes.c_int(-1)
+        ctypes.CDLL("libcudart.so.12").cudaGetDevice(ctypes.byref(dev))
+        assert dev.value == 1
+        buf.close()
+        f0.close()
+    finally:
+        torch.cuda.set_device(0)
 
 
 def test_c3_batch_properties_and_sampled_chunks(shf, filt, oracle_mod):

@@ -1,5 +1,5 @@
 // Minimal stand-in for <glm/vec2.hpp> (GLM is not installed in this image). Own code, test infrastructure only:
-// provides exactly the two-component vector operations the reference filter touches
+// provides exactly the two-component vector operations the reference filter and biome factory touch
 // (/root/reference/SuperTerrain+/SuperAlgorithm+/Host/Private/STPSingleHistogramFilter.cpp:876-878).
 #pragma once
 namespace glm {
@@ -15,4 +15,5 @@ template <typename T> constexpr tvec2<T> operator*(const tvec2<T>& a, T k) { ret
 template <typename T> constexpr tvec2<T> operator/(const tvec2<T>& a, T k) { return tvec2<T>(a.x / k, a.y / k); }
 using uvec2 = tvec2<unsigned int>;
 using vec2 = tvec2<float>;
+using ivec2 = tvec2<int>;   // STPBiomeFactory::operator()(STPSample_t*, glm::ivec2)
 }

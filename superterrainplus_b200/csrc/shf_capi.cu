@@ -67,6 +67,12 @@ struct DevBuf {
         cap = (e == cudaSuccess) ? want : 0;
         return e;
     }
+    // for buffers whose users leave them zeroed: zero-filled whenever (re)allocated
+    cudaError_t ensure_zeroed(size_t bytes, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        const cudaError_t e = ensure(bytes);
+        return e == cudaSuccess ? cudaMemsetAsync(p, 0, cap, s) : e;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -113,7 +119,8 @@ struct shf_toggles {
 struct shf_filter {
     int device = 0;
     int sm_count = 0;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0;    // per block
+    size_t smem_per_sm = 0;
     shf_toggles dbg;
 };
 
@@ -130,7 +137,7 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
-        bins, hso, gstate, evpool, rowinfo, cvt, vexit;
+        bins, hso, gstate, evpool, rowinfo, cvt, vexit, sync;
     PinBuf h_small, h_bins, h_hso;
     std::vector<uint64_t> chunk_base;  // n_chunks + 1
     uint32_t n_chunks = 0, last_w = 0, last_h = 0;
@@ -184,7 +191,7 @@ struct shf_buffer {
         done_recorded = false;
         DevBuf* d[] = {&din, &cmap, &vstart, &bitmap, &prefix, &nbiomes, &dict, &base,
                        &colmask, &rowtotal, &rowbase, &chunktotal, &chunkbase, &bins, &hso, &gstate, &hf_offsets,
-                       &evpool, &rowinfo, &cvt, &vexit};
+                       &evpool, &rowinfo, &cvt, &vexit, &sync};
         for (DevBuf* b : d) b->release();
         h_small.release();
         h_bins.release();
@@ -205,6 +212,11 @@ uint32_t shf_rows_grid(uint32_t PH, uint32_t n_chunks, int sm_count) {
     return std::max(1u, std::min(std::min(want, PH), 256u));
 }
 
+// state table + transposed masks + the staging tile of one vscan CTA (one warp)
+size_t vscan_smem(int K) {
+    return (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K + (size_t)32 * shf::kVscanStagePitch * 4;
+}
+
 size_t emit_smem(uint32_t ty, uint32_t R, int K, int FW) {
     return (size_t)ty * R * 32 * K * FW / 8 + (size_t)ty * shf::kMarchNB * shf::emit_sbuf_stride(K, FW) +
            (size_t)ty * shf::emit_act_cap(K) * 8 + 128 +
@@ -213,12 +225,14 @@ size_t emit_smem(uint32_t ty, uint32_t R, int K, int FW) {
 
 template <int K>
 int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
-    unsigned long long* counter = b->chunktotal.as<unsigned long long>() + g.n_chunks;
-    SHF_CUDA(cudaMemsetAsync(counter, 0, 8, s));
+    // sync: [0..1] the event counter (u64), [2] chunks finished, [3 + n] CTAs of chunk n finished, [3 + n_chunks + n]
+    // presence CTAs of chunk n finished; all left at zero by their kernels
+    uint32_t* sync = b->sync.as<uint32_t>();
     shf::events_kernel<K><<<dim3((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks), shf::kEventWarps * 32, 0, s>>>(
         g, b->colmask.as<uint32_t>(), b->cvt.as<uint32_t>(), b->dict.as<uint16_t>(), 32 * K,
-        b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), counter, b->rowinfo.as<uint2>(),
-        b->rowtotal.as<uint32_t>());
+        b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), reinterpret_cast<unsigned long long*>(sync),
+        b->rowinfo.as<uint2>(), b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+        b->chunktotal.as<unsigned long long>(), b->chunkbase.as<unsigned long long>(), b->hso.as<uint32_t>(), sync + 2);
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
     return SHF_OK;
@@ -240,7 +254,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     if (phase == 0) {
         const uint32_t nblk = (g.PW + shf::kVscanThreads - 1) / shf::kVscanThreads;
         const dim3 vgrid(nblk, g.n_chunks, g.vseg);
-        const size_t vsmem = (size_t)shf::kVscanThreads * (4 * 32 * K) + 4 * 32 * K + 32 * 33 * 4;
+        const size_t vsmem = vscan_smem(K);
         if (g.vseg > 1u) SHF_CUDA(b->vexit.ensure((size_t)g.n_chunks * (g.vseg - 1u) * nblk * 32 * K * 32 * 4));
         if (g.TY % 8u == 0u) {
             SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
@@ -297,6 +311,23 @@ int dispatch_chain(int K, shf_buffer* b, const Geo& g, cudaStream_t s, int phase
     return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
 }
 
+// dictionary of every chunk: presence bitmap -> popcount prefix + number of distinct values (by the chunk's last CTA)
+int launch_dictionary(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
+    const uint32_t n_chunks = g.n_chunks;
+    SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
+    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks, f->sm_count), n_chunks);
+    uint32_t* done = b->sync.as<uint32_t>() + 3u + n_chunks;
+    if (vec8)
+        shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                      b->nbiomes.as<uint32_t>(), done);
+    else
+        shf::presence_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
+                                                      b->nbiomes.as<uint32_t>(), done);
+    tls_launches++;
+    SHF_CUDA(cudaGetLastError());
+    return SHF_OK;
+}
+
 // SHF.cpp:874-880
 int validate(const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius) {
     if (!(radius > 0u && (radius & 1u) == 0u))
@@ -335,10 +366,12 @@ int prepare_common(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* i
 int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s, bool with_events = false) {
     const uint32_t n_chunks = g.n_chunks;
     SHF_CUDA(b->mark(3, s));
-    shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
-                                                  b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
-    tls_launches++;
-    SHF_CUDA(cudaGetLastError());
+    if (!with_events) {   // (events_kernel has scanned its own row totals)
+        shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+                                                      b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    }
     SHF_CUDA(b->mark(4, s));
     const size_t n_read = (size_t)n_chunks + (with_events ? 1u : 0u);
     SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, n_read * 8, cudaMemcpyDeviceToHost, s));
@@ -351,7 +384,7 @@ int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s,
             return fail(SHF_ERR_UNSUPPORTED, "presence chains per call < 2^32", "too many bin births in one batch");
         if (need > b->evpool.cap / 8) {
             SHF_CUDA(b->evpool.ensure((size_t)(need + need / 8u + 1024u) * 8));
-            const int st = dispatch_events((int)g.K, b, g, s);
+            const int st = dispatch_events((int)g.K, b, g, s);   // (same totals; chunkbase is written again as well)
             if (st != SHF_OK) return st;
         }
     }
@@ -364,8 +397,10 @@ int size_output(shf_buffer* b, const Geo& g, uint64_t* h_totals, cudaStream_t s,
     }
     const size_t total = (size_t)b->chunk_base[n_chunks];
     SHF_CUDA(b->bins.ensure(std::max<size_t>(total, 1) * sizeof(shf_bin)));
-    SHF_CUDA(cudaMemcpyAsync(b->chunkbase.p, b->chunk_base.data(), (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
-    tls_h2d += (size_t)(n_chunks + 1) * 8;
+    if (!with_events) {   // (events_kernel has left the same numbers in chunkbase)
+        SHF_CUDA(cudaMemcpyAsync(b->chunkbase.p, b->chunk_base.data(), (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
+        tls_h2d += (size_t)(n_chunks + 1) * 8;
+    }
     return SHF_OK;
 }
 
@@ -442,29 +477,14 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
     const int K = (int)g.K;
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
-    SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
-    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks, f->sm_count), n_chunks);
-    if (vec8)
-        shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
-    else
-        shf::presence_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
-    tls_launches++;
-    shf::dict_prefix_kernel<<<n_chunks, 256, 0, s>>>(b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
-                                                     b->nbiomes.as<uint32_t>());
-    tls_launches++;
-    SHF_CUDA(cudaGetLastError());
-    SHF_CUDA(b->mark(1, s));
-    int st = prepare_common(f, b, g, in_dev, vec8, s);
+    int st = launch_dictionary(f, b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
-    st = dispatch_chain(K, b, g, s, 0);
+    SHF_CUDA(b->mark(1, s));
+    st = prepare_common(f, b, g, in_dev, vec8, s);
+    if (st != SHF_OK) return st;
+    st = dispatch_chain(K, b, g, s, 0);   // (events_kernel leaves the row and chunk bases behind)
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(3, s));
-    shf::rowscan_kernel<<<n_chunks, 1024, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
-                                                  b->chunktotal.as<unsigned long long>(), b->hso.as<uint32_t>());
-    shf::chunkbase_kernel<<<1, 1024, 0, s>>>(n_chunks, b->chunktotal.as<unsigned long long>(),
-                                             b->chunkbase.as<unsigned long long>());
-    tls_launches += 2;
-    SHF_CUDA(cudaGetLastError());
     SHF_CUDA(b->mark(4, s));
     SHF_CUDA(b->mark(5, s));
     st = dispatch_chain(K, b, g, s, 1);
@@ -554,6 +574,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
+    SHF_CUDA(b->sync.ensure_zeroed(((size_t)n_chunks * 2 + 4) * 4, s));   // arrival counters, left at zero by their kernels
     SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 64));
     uint32_t* h_nbiomes;
     uint64_t* h_totals;
@@ -600,17 +621,10 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
     // ---- dictionary ----
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
-    SHF_CUDA(cudaMemsetAsync(b->bitmap.p, 0, (size_t)n_chunks * shf::kDictWords * 4, s));
-    const dim3 pgrid(shf_rows_grid(g.PH, n_chunks, f->sm_count), n_chunks);
-    if (vec8)
-        shf::presence_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
-    else
-        shf::presence_kernel<1><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>());
-    tls_launches++;
-    shf::dict_prefix_kernel<<<n_chunks, 256, 0, s>>>(b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
-                                                     b->nbiomes.as<uint32_t>());
-    tls_launches++;
-    SHF_CUDA(cudaGetLastError());
+    {
+        const int st = launch_dictionary(f, b, g, in_dev, vec8, s);
+        if (st != SHF_OK) return st;
+    }
     SHF_CUDA(b->mark(1, s));
     SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
     tls_d2h += (size_t)n_chunks * 4;
@@ -695,13 +709,16 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
         // such warps) is split into up to eight row segments per block, each replaying the 2r+1 rows above its first
         g.vseg = 1u;
         g.vseg_rows = 0u;
+        // (the kernel is a per-thread latency chain: as long as all its warps are resident at once, more and shorter
+        // ones finish sooner although every segment adds 2r+1 replayed rows)
         const uint64_t vwarps = (uint64_t)n_chunks * ((g.PW + 31u) / 32u);
-        if (!generic && vwarps < 2ull * (uint64_t)f->sm_count && !f->dbg.no_vseg) {
+        const uint64_t vresident = (uint64_t)f->sm_count * std::min<uint64_t>(32u, f->smem_per_sm / (vscan_smem(K) + 1024u));
+        if (!generic && vwarps * 2u <= vresident && !f->dbg.no_vseg) {
             uint32_t S = 8u;
             if (f->dbg.debug_vseg) S = f->dbg.debug_vseg;  // measurements only
             while (S > 1u) {
                 const uint32_t L = (((H - 1u) + S - 1u) / S + 31u) & ~31u;   // output rows per segment
-                if (L >= std::max(64u, g.span / 2u) && 1u + (S - 1u) * L < H && vwarps * S <= 4ull * (uint64_t)f->sm_count) {
+                if (L >= std::max(64u, g.span / 2u) && 1u + (S - 1u) * L < H && (vwarps * S <= vresident || f->dbg.debug_vseg)) {
                     g.vseg = S;
                     g.vseg_rows = L;
                     break;
@@ -953,6 +970,8 @@ int shf_filter_create(shf_filter** out, int device) {
         return fail(SHF_ERR_CUDA, "cudaDeviceGetAttribute", cudaGetErrorString(e));
     }
     f->smem_optin = (size_t)v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess) v = (int)f->smem_optin;
+    f->smem_per_sm = (size_t)v;
     auto env_u32 = [](const char* name) {
         const char* e = getenv(name);
         return e ? (uint32_t)std::max(1, atoi(e)) : 0u;

@@ -191,23 +191,16 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
     return E;
 }
 
-// rowinfo(n, y) = (first record of the row in the pool, number of records). counter[0] = records handed out so far;
-// a row whose slot would end beyond `pool_cap` writes nothing (the host grows the pool and runs the kernel again).
+// the event list of one output row (one warp): rowinfo(n, y) = (first record of the row in the pool, number of records).
+// counter[0] = records handed out so far; a row whose slot would end beyond `pool_cap` writes nothing (the host grows
+// the pool and runs the kernel again).
 template <int K>
-__global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K == 4 ? 4 : 3)
-    events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint32_t* __restrict__ cvt,
-                  const uint16_t* __restrict__ dict, uint32_t dict_stride,
-                  uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
-                  uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal) {
-    __shared__ uint2 stage_all[kEventWarps][kEventStage];
-    __shared__ uint16_t tab_all[kEventWarps][32 * K];
-    __shared__ __align__(16) uint32_t mstage_all[kEventWarps][2 * event_group(K) * 32 * K];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t n = blockIdx.y, y = blockIdx.x * kEventWarps + warp;
-    if (y >= g.H) return;
-    uint2* stage = stage_all[warp];
-    uint16_t* tab = tab_all[warp];
-    uint32_t* mstage = mstage_all[warp];
+__device__ __forceinline__ void events_row(const Geo& g, uint32_t n, uint32_t y, uint32_t lane,
+                                           const uint32_t* __restrict__ colmask, const uint32_t* __restrict__ cvt,
+                                           const uint16_t* __restrict__ dict, uint32_t dict_stride,
+                                           uint2* __restrict__ pool, unsigned long long pool_cap,
+                                           unsigned long long* __restrict__ counter, uint2* __restrict__ rowinfo,
+                                           uint32_t* __restrict__ rowtotal, uint2* stage, uint16_t* tab, uint32_t* mstage) {
     const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * ((g.PW + 31u) / 32u) * 32u * K;  // transposed masks
     const uint32_t* cv = cvt + (size_t)n * g.PW * g.cv_pitch;
     uint32_t item[K];
@@ -233,6 +226,57 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     } else {
         uint32_t again = 0u;
         (void)walk_row<K>(g, y, lane, cmask_row, cv, item, tab, mstage, pool + first, E, again);
+    }
+}
+
+// One warp per output row. The CTA that finishes a chunk last (sync[1 + n]) scans the chunk's bins per row into the
+// first-bin index of every row (rowbase), the chunk total and the closing offset entry; the CTA that finishes the last
+// chunk (sync[0]) scans the chunk totals into the first-bin index of every chunk and hands the event count to the host
+// (chunktotal[n_chunks]). Both re-arm their counters: a call needs neither a memset nor separate scan launches.
+template <int K>
+__global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K == 4 ? 4 : 3)
+    events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint32_t* __restrict__ cvt,
+                  const uint16_t* __restrict__ dict, uint32_t dict_stride,
+                  uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
+                  uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal, uint32_t* __restrict__ rowbase,
+                  unsigned long long* __restrict__ chunktotal, unsigned long long* __restrict__ chunkbase,
+                  uint32_t* __restrict__ hso, uint32_t* __restrict__ sync) {
+    __shared__ uint2 stage_all[kEventWarps][kEventStage];
+    __shared__ uint16_t tab_all[kEventWarps][32 * K];
+    __shared__ __align__(16) uint32_t mstage_all[kEventWarps][2 * event_group(K) * 32 * K];
+    __shared__ unsigned long long warp_part[32];
+    __shared__ uint32_t last_flag;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.y, y = blockIdx.x * kEventWarps + warp;
+    if (y < g.H) events_row<K>(g, n, y, lane, colmask, cvt, dict, dict_stride, pool, pool_cap, counter, rowinfo, rowtotal,
+                               stage_all[warp], tab_all[warp], mstage_all[warp]);
+    // ---- last CTA of the chunk: first-bin index of every row ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0u) last_flag = atomicAdd(&sync[1u + n], 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    // (u32 row bases: garbage if the chunk total overflows 32 bits; the host checks the total)
+    const unsigned long long total = cta_exclusive_scan(rowtotal + (size_t)n * g.H, rowbase + (size_t)n * g.H, g.H, warp_part);
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        chunktotal[n] = total;
+        hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)total;
+        sync[1u + n] = 0u;
+        __threadfence();
+        last_flag = atomicAdd(&sync[0], 1u) == gridDim.y - 1u;
+    }
+    __syncthreads();
+    if (!last_flag) return;
+    // ---- last chunk of the call: first-bin index of every chunk ----
+    __threadfence();
+    const unsigned long long all = cta_exclusive_scan(chunktotal, chunkbase, g.n_chunks, warp_part);
+    if (threadIdx.x == 0u) {
+        chunkbase[g.n_chunks] = all;
+        chunktotal[g.n_chunks] = *counter;   // records asked for by this call (read by the host)
+        *counter = 0ull;
+        sync[0] = 0u;
     }
 }
 

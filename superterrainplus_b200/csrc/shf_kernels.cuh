@@ -60,9 +60,15 @@ struct Geo {
 // dictionary
 // ------------------------------------------------------------------------------------------------------------------
 // V = samples per load: 8 (one 16-byte load; needs a 16-byte aligned view and row stride) or 1
+// The CTA that finishes a chunk last (arrival counter `done[n]`) turns the chunk's bitmap into the dictionary: exclusive
+// prefix of the popcounts over the 2048 words and the number of distinct values, and re-arms the counter.
 template <int V>
-__global__ void presence_kernel(const uint16_t* __restrict__ in, Geo g, uint32_t* __restrict__ bitmap) {
+__global__ void __launch_bounds__(256) presence_kernel(const uint16_t* __restrict__ in, Geo g, uint32_t* __restrict__ bitmap,
+                                                       uint32_t* __restrict__ prefix, uint32_t* __restrict__ n_biomes,
+                                                       uint32_t* __restrict__ done) {
     __shared__ uint32_t bm[kDictWords];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t is_last;
     const uint32_t n = blockIdx.y;
     for (int i = threadIdx.x; i < kDictWords; i += blockDim.x) bm[i] = 0u;
     __syncthreads();
@@ -121,28 +127,29 @@ __global__ void presence_kernel(const uint16_t* __restrict__ in, Geo g, uint32_t
         if (lo0) atomicOr(&bitmap[(size_t)n * kDictWords], lo0);
         if (lo1) atomicOr(&bitmap[(size_t)n * kDictWords + 1], lo1);
     }
-    if (!__syncthreads_or(big ? 1 : 0)) return;
-    for (int i = threadIdx.x; i < kDictWords; i += blockDim.x)
-        if (bm[i]) atomicOr(&bitmap[(size_t)n * kDictWords + i], bm[i]);
-}
-
-// one CTA of 256 threads per chunk: exclusive prefix of popcounts over the 2048 bitmap words, and the biome total
-__global__ void dict_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix,
-                                   uint32_t* __restrict__ n_biomes) {
-    __shared__ uint32_t part[256];
-    const uint32_t n = blockIdx.x, t = threadIdx.x;
-    const uint32_t* bm = bitmap + (size_t)n * kDictWords;
+    if (__syncthreads_or(big ? 1 : 0)) {
+        for (int i = threadIdx.x; i < kDictWords; i += blockDim.x)
+            if (bm[i]) atomicOr(&bitmap[(size_t)n * kDictWords + i], bm[i]);
+    }
+    // ---- the last CTA of the chunk: dictionary prefix ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0u) is_last = atomicAdd(&done[n], 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const uint32_t t = threadIdx.x;
+    const uint32_t* words = bitmap + (size_t)n * kDictWords;
     uint32_t local[8], sum = 0u;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         local[i] = sum;
-        sum += __popc(bm[t * 8 + i]);
+        sum += __popc(__ldcg(words + t * 8 + i));   // (other CTAs' atomics: read past the L1)
     }
     part[t] = sum;
     __syncthreads();
-    // simple Hillis-Steele over 256 partial sums
-    for (int off = 1; off < 256; off <<= 1) {
-        uint32_t v = (t >= (uint32_t)off) ? part[t - off] : 0u;
+    for (int off = 1; off < 256; off <<= 1) {   // Hillis-Steele over the 256 partial sums
+        const uint32_t v = (t >= (uint32_t)off) ? part[t - off] : 0u;
         __syncthreads();
         part[t] += v;
         __syncthreads();
@@ -150,7 +157,8 @@ __global__ void dict_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t
     const uint32_t excl = part[t] - sum;
 #pragma unroll
     for (int i = 0; i < 8; i++) prefix[(size_t)n * kDictWords + t * 8 + i] = excl + local[i];
-    if (t == 255) n_biomes[n] = part[255];
+    if (t == 255u) n_biomes[n] = part[255];
+    if (t == 0u) done[n] = 0u;
 }
 
 // remap samples to compact ids; CTA x==0 of every chunk also writes the dictionary (compact id -> sample value)
@@ -230,11 +238,15 @@ __global__ void remap_kernel(const uint16_t* __restrict__ in, Geo g, const uint3
 // compact id `id` occurs in column 32*block + j, rows [y, y+2r]. They are kept incrementally in shared memory (a count
 // reaching / leaving zero flips one bit with a shared-memory atomic), so events_kernel reads them lane = id as they are.
 // (free functions taking plain values: a noinline member would force the whole state struct into local memory)
+constexpr uint32_t kVscanStageRows = 16;                       // rows staged per flush (a 64-byte line per column)
+constexpr uint32_t kVscanStagePitch = kVscanStageRows + 1;     // words per staged column (odd: conflict-free pushes)
 __device__ __noinline__ void vscan_flush(const uint32_t* stg, uint32_t* cv_blk, uint32_t cv_pitch, uint32_t ncols,
                                          uint32_t line0, uint32_t lane) {
     __syncwarp();
-    uint32_t* dst = cv_blk + line0 + lane;
-    for (uint32_t col = 0u; col < ncols; col++) dst[(size_t)col * cv_pitch] = stg[lane * 33u + col];
+    const uint32_t row = lane & (kVscanStageRows - 1u);
+    uint32_t* dst = cv_blk + line0 + row;
+    // two columns per store instruction: lanes 0-15 the even one, lanes 16-31 the odd one
+    for (uint32_t col = lane >> 4; col < ncols; col += 2u) dst[(size_t)col * cv_pitch] = stg[col * kVscanStagePitch + row];
     __syncwarp();
 }
 // a tile's base vector: the window counts (<= 2r+1) by compact id, as bytes (fw = 8) or 16-bit words (fw = 16)
@@ -320,12 +332,16 @@ struct VscanState {
         __syncwarp();
     }
     // (compact id | chain start << 16) of every cell goes to a column-major map (a column's window is contiguous for
-    // events_kernel). 32 rows are staged in shared memory ([row][33] words) and leave as one 128-byte line per column.
+    // events_kernel). 16 rows are staged in shared memory ([column][17] words) and leave as one 64-byte line per column
+    // (a smaller stage than a full 128-byte line: 20 instead of 17 of these one-warp CTAs fit an SM, and the kernel is
+    // bound by the latency of its per-row chain, i.e. by the warps in flight).
     uint32_t* stg;        // the warp's staging tile
     uint32_t* cv_blk;     // the block's first column in the map, at index 0
     uint32_t cv_pitch, ncols;
     __device__ __forceinline__ void flush(uint32_t line0) const { vscan_flush(stg, cv_blk, cv_pitch, ncols, line0, lane); }
-    __device__ __forceinline__ void push(uint32_t idx, uint32_t value) const { stg[(idx & 31u) * 33u + lane] = value; }
+    __device__ __forceinline__ void push(uint32_t idx, uint32_t value) const {
+        stg[lane * kVscanStagePitch + (idx & (kVscanStageRows - 1u))] = value;
+    }
 
     uint32_t fw;
     __device__ __forceinline__ void dump(uint8_t* dst8) const { vscan_dump<K>(st, dst8, fw); }
@@ -387,14 +403,14 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 vs.push(ci, s_in[j] | (vs.enter(s_in[j], p + j) << 16));
-                if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+                if ((++ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
             }
             in += 8 * P;
         }
         for (; p <= two_r; p++) {
             const uint32_t sv = *in;
             vs.push(ci, sv | (vs.enter(sv, p) << 16));
-            if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+            if ((++ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
             in += P;
         }
         vs.store_mask(mout);
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
                 }
             }
             ci += 8u;
-            if ((ci & 31u) == 0u) vs.flush(ci - 32u);
+            if ((ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
             in += 8 * P;
             out += 8 * P;
             mout += 8 * mstep;
@@ -469,7 +485,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     for (; y < y_end; y++) {
         const uint32_t sv = *in;
         vs.push(ci, sv | (vs.step(sv, *out, two_r + y) << 16));
-        if ((++ci & 31u) == 0u) vs.flush(ci - 32u);
+        if ((++ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
         vs.store_mask(mout);
         in += P;
         out += P;
@@ -480,7 +496,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             next_dump += g.TY;
         }
     }
-    if (ci & 31u) vs.flush(ci & ~31u);
+    if (ci & (kVscanStageRows - 1u)) vs.flush(ci & ~(kVscanStageRows - 1u));
     // exit state for the segment below: (count, start) of every value in this column
     if (seg + 1u < n_seg) {
         uint32_t* ex = vexit + ((((size_t)n * (n_seg - 1u) + seg) * gridDim.x + blockIdx.x) * Bpad) * T + lane;
@@ -558,6 +574,37 @@ constexpr int kMarchNB = 16;
 // ------------------------------------------------------------------------------------------------------------------
 // first-bin index of every row (exclusive scan of the bins-per-row), chunk totals, the closing offset entry
 // ------------------------------------------------------------------------------------------------------------------
+// Exclusive scan of `count` 32- or 64-bit values by one CTA of `T` threads (T <= 1024, a multiple of 32), 64-bit sums:
+// out[i] = sum of in[0..i) (+ nothing else), returns the total to every thread. `warp_part` = 32 shared 64-bit words.
+template <typename TIn, typename TOut>
+__device__ __forceinline__ unsigned long long cta_exclusive_scan(const TIn* in, TOut* out, uint32_t count,
+                                                                 unsigned long long* warp_part) {
+    const uint32_t t = threadIdx.x, T = blockDim.x, lane = t & 31u, warp = t >> 5, n_warps = T >> 5;
+    unsigned long long carry = 0ull;
+    for (uint32_t i0 = 0u; i0 < count; i0 += T) {
+        const uint32_t i = i0 + t;
+        const unsigned long long v = i < count ? (unsigned long long)__ldcg(in + i) : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long u = __shfl_up_sync(kFull, incl, off);
+            if (lane >= (uint32_t)off) incl += u;
+        }
+        __syncthreads();   // warp_part of the previous round has been read
+        if (lane == 31u) warp_part[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0ull, round = 0ull;
+        for (uint32_t w = 0u; w < n_warps; w++) {
+            const unsigned long long u = warp_part[w];
+            if (w < warp) before += u;
+            round += u;
+        }
+        if (i < count) out[i] = (TOut)(carry + before + incl - v);
+        carry += round;
+    }
+    return carry;
+}
+
 __global__ void rowscan_kernel(Geo g, const uint32_t* __restrict__ rowtotal, uint32_t* __restrict__ rowbase,
                                unsigned long long* __restrict__ chunktotal, uint32_t* __restrict__ hso) {
     __shared__ unsigned long long part[1024];

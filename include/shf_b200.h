@@ -183,6 +183,48 @@ SHF_API void shf_heightfield_destroy(shf_heightfield* generator);
 SHF_API int shf_heightfield_run(shf_heightfield* generator, shf_buffer* buffer, uint32_t first_chunk, uint32_t n_chunks,
                                 const float* offsets_xy, float* height_dev, void* stream);
 
+/* ---- biome-map producer on the device (additive) ----
+ * What STPBiomeFactory::operator()(STPSample_t* biomemap, glm::ivec2 offset) computes on the CPU
+ * (SuperTerrain+/SuperTerrain+/Private/World/Diversity/STPBiomeFactory.cpp:24-42: biomemap[x + z * dim.x] =
+ * tree.retrieve(x + offset.x, 0, z + offset.y) through a chain of STPLayer objects, STPLayer.cpp:118-196), written
+ * straight into DEVICE memory, so that the uint16 sample map the filter reads never exists on the host. The reference's
+ * layers are virtual C++ classes supplied by the application (STPBiomeFactory::supply()); here the chain is DATA: a list
+ * of the demo's layer kinds (SuperDemo+/World/Layers/) with their salts, in construction order -- every layer names its
+ * ascendant by index, the last layer is the root the factory samples (STPAllLayers.cpp:61-109). */
+enum shf_biome_layer_kind {
+    SHF_LAYER_CONTINENT = 0,    /* STPContinentLayer.h:17-23, no ascendant */
+    SHF_LAYER_SCALE_NORMAL = 1, /* STPScaleLayer.h:31-98, STPScaleType::NORMAL */
+    SHF_LAYER_SCALE_FUZZY = 2,  /* STPScaleLayer.h:31-98, STPScaleType::FUZZY */
+    SHF_LAYER_LAND = 3,         /* STPXCrossLayer.h:26-37 + STPLandLayer.h:20-70 */
+    SHF_LAYER_ISLAND = 4,       /* STPCrossLayer.h:26-37 + STPIslandLayer.h:20-27 */
+    SHF_LAYER_VORONOI = 5       /* STPVoronoiLayer.h:56-101 with Is3D = false */
+};
+typedef struct shf_biome_layer {
+    uint32_t kind;   /* shf_biome_layer_kind */
+    uint32_t parent; /* index of the ascendant layer (< this layer's index); ignored for SHF_LAYER_CONTINENT */
+    uint64_t salt;   /* STPLayer's salt; the layer seed is STPLayer::seedLayer(global seed, salt) */
+} shf_biome_layer;
+/* Sample values the layers test and produce: STPBiomeRegistry::{Ocean, Plains, Forest, FrozenOcean, WarmOcean,
+ * LukewarmOcean, ColdOcean}.ID (SuperDemo+/World/Biomes/STPBiomeRegistry.cpp:112-116; loaded from Biome.ini by the demo). */
+typedef struct shf_biome_ids {
+    uint16_t ocean, plains, forest, frozen_ocean, warm_ocean, lukewarm_ocean, cold_ocean;
+} shf_biome_ids;
+typedef struct shf_biome_factory shf_biome_factory; /* <-> STPBiomeFactory (STPBiomeFactory.h:21-73) */
+
+/* STPBiomeFactory(dimension) + the chain supply() would build. voronoi_seed = std::hash<STPSeed_t>{}(global_seed)
+ * (STPVoronoiLayer.h:52), which is standard-library defined: the identity with libstdc++. */
+SHF_API int shf_biome_factory_create(shf_biome_factory** out, shf_filter* filter, uint32_t width, uint32_t height,
+                                     const shf_biome_layer* layers, uint32_t n_layers, uint64_t global_seed,
+                                     uint64_t voronoi_seed, const shf_biome_ids* ids);
+SHF_API void shf_biome_factory_destroy(shf_biome_factory* factory);
+/* operator()(biomemap, offset) for n_maps offsets at once. biomemap_dev: DEVICE memory, map i at biomemap_dev +
+ * i * map_stride, row z of a map at + z * row_stride (0 = width), i.e. a map may be a window of a larger image -- e.g.
+ * only the (W+2r) x (H+2r) cells the filter reads of a merged neighbourhood map. offsets_xz: HOST array of 2 * n_maps
+ * ints, the world coordinate of every map's first cell. Work is enqueued on `stream` (cudaStream_t); the call returns
+ * without waiting for it. One call at a time per factory. */
+SHF_API int shf_biome_factory_run(shf_biome_factory* factory, uint16_t* biomemap_dev, uint32_t row_stride,
+                                  uint64_t map_stride, uint32_t n_maps, const int32_t* offsets_xz, void* stream);
+
 /* Message of the last failure on the calling thread: "<expression>: <description>" in the spirit of
  * STPException::STPBasic::what(), so that the C++ shim can throw the matching exception type. */
 SHF_API const char* shf_last_error(void);

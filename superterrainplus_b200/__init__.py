@@ -11,8 +11,11 @@ the CUDA library and a device and raises otherwise.
 from .api import (  # noqa: F401
     BIN_DTYPE,
     BIOME_PROPERTY_DTYPE,
+    STPBiomeFactory,
     STPCUDAError,
     STPInvalidEnum,
+    STPLayerChainBuilder,
+    STPLayerKind,
     STPMultiBiomeHeightfield,
     STPNearestNeighbourInformation,
     STPNumericDomainError,
@@ -24,6 +27,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BIN_DTYPE", "BIOME_PROPERTY_DTYPE", "STPCUDAError", "STPMultiBiomeHeightfield", "STPInvalidEnum", "STPNearestNeighbourInformation", "STPNumericDomainError",
+    "BIN_DTYPE", "BIOME_PROPERTY_DTYPE", "STPBiomeFactory", "STPLayerChainBuilder", "STPLayerKind", "STPCUDAError", "STPMultiBiomeHeightfield", "STPInvalidEnum", "STPNearestNeighbourInformation", "STPNumericDomainError",
     "STPSingleHistogram", "STPSingleHistogramFilter", "STPUnsupportedError", "library", "library_path",
 ]

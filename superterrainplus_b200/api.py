@@ -36,6 +36,7 @@ C_ABI_SYMBOLS = (
     "shf_run_neighbours_device", "shf_run_multi", "shf_buffer_read_device",
     "shf_buffer_chunk_base", "shf_last_error", "shf_stats_reset", "shf_stats_get", "shf_buffer_last_plan",
     "shf_set_profiling", "shf_buffer_phase_ms", "shf_buffer_phase_history", "shf_heightfield_create", "shf_heightfield_destroy", "shf_heightfield_run",
+    "shf_biome_factory_create", "shf_biome_factory_destroy", "shf_biome_factory_run",
 )
 PHASES = ("dictionary", "remap_vscan", "events", "rowscan", "host_gap", "emit")
 
@@ -114,6 +115,10 @@ def library() -> ctypes.CDLL:
     lib.shf_heightfield_destroy.argtypes = [vp]
     lib.shf_heightfield_destroy.restype = None
     lib.shf_heightfield_run.argtypes = [vp, vp, u32, u32, vp, vp, vp]
+    lib.shf_biome_factory_create.argtypes = [P(vp), vp, u32, u32, vp, u32, u64, u64, vp]
+    lib.shf_biome_factory_destroy.argtypes = [vp]
+    lib.shf_biome_factory_destroy.restype = None
+    lib.shf_biome_factory_run.argtypes = [vp, vp, u32, u64, u32, vp, vp]
     _lib = lib
     return lib
 
@@ -402,3 +407,83 @@ class STPMultiBiomeHeightfield:
             raise ValueError("offsets_xy must hold one (x, y) pair per chunk")
         _check(library().shf_heightfield_run(self._h, filter_buffer._h, first_chunk, n_chunks, off.ctypes.data,
                                              height_device_ptr, stream))
+
+
+# shf_biome_layer / shf_biome_ids of include/shf_b200.h
+BIOME_LAYER_DTYPE = np.dtype([("kind", "<u4"), ("parent", "<u4"), ("salt", "<u8")])
+BIOME_IDS_DTYPE = np.dtype([(n, "<u2") for n in ("ocean", "plains", "forest", "frozen_ocean", "warm_ocean", "lukewarm_ocean",
+                                                  "cold_ocean")])
+
+
+class STPLayerKind(enum.IntEnum):
+    """The demo's layer classes this producer implements (SuperDemo+/World/Layers/)."""
+
+    Continent = 0
+    ScaleNormal = 1
+    ScaleFuzzy = 2
+    Land = 3
+    Island = 4
+    Voronoi = 5
+
+
+class STPBiomeFactory:
+    """Biome-map producer on the device (additive; shf_biome_factory_*) with the call shape of
+    STPDiversity::STPBiomeFactory (STPBiomeFactory.h:21-73): constructed with the biome map dimension, called with a map
+    and the world offset of its first cell. The layer chain the reference builds in supply() out of virtual STPLayer
+    objects is given as data: ``layers`` = sequence of (STPLayerKind, salt) or (STPLayerKind, salt, ascendant index), in
+    construction order, the last one being the root; a missing ascendant index means "the layer before"."""
+
+    def __init__(self, filt: "STPSingleHistogramFilter", dimension: Tuple[int, int], layers: Sequence, global_seed: int,
+                 ids, voronoi_seed: Optional[int] = None):
+        arr = np.zeros(len(layers), dtype=BIOME_LAYER_DTYPE)
+        for i, ly in enumerate(layers):
+            arr[i] = (int(ly[0]), int(ly[2]) if len(ly) > 2 else max(i - 1, 0), int(ly[1]))
+        idv = np.zeros(1, dtype=BIOME_IDS_DTYPE)
+        idv[0] = tuple(int(v) for v in ids)
+        self.BiomeDimension = (int(dimension[0]), int(dimension[1]))
+        self._h = ctypes.c_void_p()
+        # std::hash<STPSeed_t> is the identity with libstdc++ (STPVoronoiLayer.h:52)
+        vs = global_seed if voronoi_seed is None else voronoi_seed
+        _check(library().shf_biome_factory_create(ctypes.byref(self._h), filt._h, self.BiomeDimension[0],
+                                                  self.BiomeDimension[1], arr.ctypes.data, len(arr),
+                                                  global_seed & 0xFFFFFFFFFFFFFFFF, vs & 0xFFFFFFFFFFFFFFFF,
+                                                  idv.ctypes.data))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            library().shf_biome_factory_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, biomemap_device_ptr: int, offsets_xz, row_stride: int = 0, map_stride: int = 0,
+                 stream: int = 0) -> None:
+        """operator()(biomemap, offset) for one or many offsets: map i is written to device memory at
+        biomemap_device_ptr + 2 * i * map_stride bytes (default: maps packed back to back), enqueued on `stream`."""
+        off = np.ascontiguousarray(offsets_xz, dtype=np.int32).reshape(-1, 2)
+        stride = map_stride or (row_stride or self.BiomeDimension[0]) * self.BiomeDimension[1]
+        _check(library().shf_biome_factory_run(self._h, biomemap_device_ptr, row_stride, stride, len(off),
+                                               off.ctypes.data, stream))
+
+
+class STPLayerChainBuilder(STPBiomeFactory):
+    """The demo's chain (STPDemo::STPLayerChainBuilder, SuperDemo+/World/Layers/STPAllLayers.cpp:61-109): continent ->
+    fuzzy scale -> land -> scale -> 3 x land -> island -> 3 x scale -> 3 x Voronoi, with the demo's salts."""
+
+    CHAIN = (
+        (STPLayerKind.Continent, 23457829), (STPLayerKind.ScaleFuzzy, 875944), (STPLayerKind.Land, 5748329),
+        (STPLayerKind.ScaleNormal, 8947358941), (STPLayerKind.Land, 361249673), (STPLayerKind.Land, 8769575),
+        (STPLayerKind.Land, 43562783426564), (STPLayerKind.Island, 74368),
+        (STPLayerKind.ScaleNormal, 1), (STPLayerKind.ScaleNormal, 2), (STPLayerKind.ScaleNormal, 3),
+        (STPLayerKind.Voronoi, 4), (STPLayerKind.Voronoi, 5), (STPLayerKind.Voronoi, 6),
+    )
+    # SuperDemo+/Biome.ini: ocean 0, plains 1, forest 3; the other shallow oceans of the registry are never given an id
+    IDS = (0, 1, 3, 0, 0, 0, 0)
+
+    def __init__(self, filt: "STPSingleHistogramFilter", dimension: Tuple[int, int], global_seed: int, ids=None):
+        super().__init__(filt, dimension, self.CHAIN, global_seed, ids or self.IDS)
+        self.GlobalSeed = global_seed

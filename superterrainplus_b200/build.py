@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libshf_b200.so")
 SOURCES = [os.path.join(_CSRC, "shf_capi.cu")]
-DEPENDS = SOURCES + [os.path.join(_CSRC, "shf_kernels.cuh"), os.path.join(_CSRC, "shf_generic.cuh"), os.path.join(_CSRC, "shf_events.cuh"), os.path.join(_CSRC, "shf_heightfield.cuh"), os.path.join(_HERE, "..", "include", "shf_b200.h")]
+DEPENDS = SOURCES + [os.path.join(_CSRC, "shf_kernels.cuh"), os.path.join(_CSRC, "shf_generic.cuh"), os.path.join(_CSRC, "shf_events.cuh"), os.path.join(_CSRC, "shf_heightfield.cuh"), os.path.join(_CSRC, "shf_biome.cuh"), os.path.join(_HERE, "..", "include", "shf_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",

@@ -5,6 +5,7 @@
 #include "shf_events.cuh"
 #include "shf_generic.cuh"
 #include "shf_heightfield.cuh"
+#include "shf_biome.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -130,6 +131,21 @@ struct shf_heightfield {
     size_t smem_optin = 0;
     uint32_t n_table = 0, grad_size = 0;
     DevBuf table, perm, grad;
+};
+
+// the biome-map producer: the layer chain, its seeds and per-layer device scratch
+struct shf_biome_factory {
+    int device = 0;
+    int sm_count = 0;
+    uint32_t width = 0, height = 0;
+    std::vector<shf_biome_layer> layers;
+    std::vector<uint64_t> seeds;          // STPLayer::seedLayer(global seed, salt) of every layer
+    uint64_t voronoi_seed = 0;
+    shf::BiomeIds ids{};
+    std::vector<DevBuf> grid;             // per layer: the cells its descendants read, all maps of a batch
+    DevBuf rects, jitter;
+    PinBuf h_rects;
+    cudaEvent_t rects_free = nullptr;     // the upload of the previous call's rectangles has left the pinned block
 };
 
 struct shf_buffer {
@@ -270,8 +286,8 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         if (g.vseg > 1u) {
             // chain starts the row segments could not know
             const uint32_t rows = g.H - (1u + g.vseg_rows);
-            shf::vpatch_kernel<<<dim3((rows + 255u) / 256u, g.PW, g.n_chunks), 256, 0, s>>>(g, nblk, b->cvt.as<uint32_t>(),
-                                                                                             b->vexit.as<uint32_t>());
+            shf::vpatch_kernel<<<dim3((rows + 511u) / 512u, (g.PW + 3u) / 4u, g.n_chunks), 256, 0, s>>>(
+                g, nblk, b->cvt.as<uint32_t>(), b->vexit.as<uint32_t>());
             tls_launches++;
         }
         tls_launches++;
@@ -1196,6 +1212,157 @@ int shf_heightfield_run(shf_heightfield* h, shf_buffer* b, uint32_t first_chunk,
         height_dev);
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
+    return SHF_OK;
+}
+
+// STPLayer::mixSeed / seedLayer (STPLayer.cpp:143-151,178-182) on the host: one seed per layer
+static uint64_t biome_mix_host(uint64_t s, uint64_t fac) {
+    s *= s * 6364136223846793005ull + 1442695040888963407ull;
+    return s + fac;
+}
+
+int shf_biome_factory_create(shf_biome_factory** out, shf_filter* f, uint32_t width, uint32_t height,
+                             const shf_biome_layer* layers, uint32_t n_layers, uint64_t global_seed, uint64_t voronoi_seed,
+                             const shf_biome_ids* ids) {
+    if (!out || !f || !layers || !ids) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    *out = nullptr;
+    // STPBiomeFactory.cpp:20-22
+    if (width == 0u || height == 0u)
+        return fail(SHF_ERR_NUMERIC_DOMAIN, "dimension.x > 0u && dimension.y > 0u",
+                    "Biomemap should have strictly positive dimension in both vector components");
+    if (n_layers == 0u || n_layers > 1024u) return fail(SHF_ERR_INVALID_ARGUMENT, "0 < n_layers <= 1024", "bad layer count");
+    for (uint32_t i = 0; i < n_layers; i++) {
+        if (layers[i].kind > SHF_LAYER_VORONOI)
+            return fail(SHF_ERR_INVALID_ENUM, "shf_biome_layer_kind", "value is not a layer kind this producer implements");
+        if (layers[i].kind != SHF_LAYER_CONTINENT && layers[i].parent >= i)
+            return fail(SHF_ERR_INVALID_ARGUMENT, "layers[i].parent < i", "an ascendant must precede its descendants");
+    }
+    shf_biome_factory* bf = new (std::nothrow) shf_biome_factory();
+    if (!bf) return fail(SHF_ERR_INVALID_ARGUMENT, "new shf_biome_factory", "out of host memory");
+    bf->device = f->device;
+    bf->sm_count = f->sm_count;
+    bf->width = width;
+    bf->height = height;
+    bf->layers.assign(layers, layers + n_layers);
+    bf->seeds.resize(n_layers);
+    for (uint32_t i = 0; i < n_layers; i++) {
+        const uint64_t salt = layers[i].salt;
+        uint64_t mid = biome_mix_host(salt, salt);
+        mid = biome_mix_host(mid, mid);
+        mid = biome_mix_host(mid, mid);
+        uint64_t s = biome_mix_host(global_seed, mid);
+        s = biome_mix_host(s, mid);
+        bf->seeds[i] = biome_mix_host(s, mid);
+    }
+    bf->voronoi_seed = voronoi_seed;
+    bf->ids = shf::BiomeIds{ids->ocean, ids->plains, ids->forest, ids->frozen_ocean, ids->warm_ocean, ids->lukewarm_ocean,
+                            ids->cold_ocean};
+    bf->grid.resize(n_layers);
+    *out = bf;
+    return SHF_OK;
+}
+
+void shf_biome_factory_destroy(shf_biome_factory* bf) {
+    if (!bf) return;
+    {
+        DeviceGuard guard(bf->device);
+        for (DevBuf& g : bf->grid) g.release();
+        bf->rects.release();
+        bf->jitter.release();
+        bf->h_rects.release();
+        if (bf->rects_free) cudaEventDestroy(bf->rects_free);
+    }
+    delete bf;
+}
+
+int shf_biome_factory_run(shf_biome_factory* bf, uint16_t* biomemap_dev, uint32_t row_stride, uint64_t map_stride,
+                          uint32_t n_maps, const int32_t* offsets_xz, void* stream) {
+    if (!bf || !biomemap_dev || !offsets_xz) return fail(SHF_ERR_INVALID_ARGUMENT, "arguments != NULL", "null argument");
+    if (n_maps == 0u || n_maps > 65535u) return fail(SHF_ERR_INVALID_ARGUMENT, "0 < n_maps <= 65535", "bad map count");
+    if (row_stride == 0u) row_stride = bf->width;
+    if (row_stride < bf->width) return fail(SHF_ERR_INVALID_ARGUMENT, "row_stride >= BiomeDimension.x", "row stride too small");
+    DeviceGuard guard(bf->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t L = (uint32_t)bf->layers.size();
+    // ---- the rectangle every layer must supply, per map, from the root down ----
+    if (!bf->rects_free) SHF_CUDA(cudaEventCreateWithFlags(&bf->rects_free, cudaEventDisableTiming));
+    else SHF_CUDA(cudaEventSynchronize(bf->rects_free));
+    const size_t n_rects = (size_t)L * n_maps;
+    SHF_CUDA(bf->h_rects.ensure(n_rects * sizeof(shf::BiomeRect)));
+    SHF_CUDA(bf->rects.ensure(n_rects * sizeof(shf::BiomeRect)));
+    shf::BiomeRect* R = bf->h_rects.as<shf::BiomeRect>();
+    std::vector<uint64_t> max_cells(L, 0ull);
+    for (uint32_t m = 0; m < n_maps; m++) {
+        struct Box { int64_t x0, z0, x1, z1; bool used; };   // inclusive
+        std::vector<Box> box(L, Box{0, 0, 0, 0, false});
+        box[L - 1u] = Box{offsets_xz[2 * m], offsets_xz[2 * m + 1], (int64_t)offsets_xz[2 * m] + bf->width - 1,
+                          (int64_t)offsets_xz[2 * m + 1] + bf->height - 1, true};
+        for (uint32_t i = L; i-- > 0u;) {
+            const Box& b = box[i];
+            if (!b.used || bf->layers[i].kind == SHF_LAYER_CONTINENT) continue;
+            Box need{};
+            switch (bf->layers[i].kind) {
+                case SHF_LAYER_SCALE_NORMAL:
+                case SHF_LAYER_SCALE_FUZZY: need = Box{b.x0 >> 1, b.z0 >> 1, (b.x1 + 1) >> 1, (b.z1 + 1) >> 1, true}; break;
+                case SHF_LAYER_VORONOI: need = Box{(b.x0 - 2) >> 2, (b.z0 - 2) >> 2, ((b.x1 - 2) >> 2) + 1, ((b.z1 - 2) >> 2) + 1, true}; break;
+                default: need = Box{b.x0 - 1, b.z0 - 1, b.x1 + 1, b.z1 + 1, true}; break;   // cross / X-cross layers
+            }
+            Box& p = box[bf->layers[i].parent];
+            if (!p.used) p = need;
+            else p = Box{std::min(p.x0, need.x0), std::min(p.z0, need.z0), std::max(p.x1, need.x1), std::max(p.z1, need.z1), true};
+        }
+        for (uint32_t i = 0; i < L; i++) {
+            const Box& b = box[i];
+            if (b.used && (b.x0 < INT32_MIN || b.x1 > INT32_MAX || b.z0 < INT32_MIN || b.z1 > INT32_MAX))
+                return fail(SHF_ERR_INVALID_ARGUMENT, "coordinates fit int", "offset + dimension overflows the layer coordinates");
+            shf::BiomeRect r{0, 0, 0u, 0u};
+            if (b.used) r = shf::BiomeRect{(int32_t)b.x0, (int32_t)b.z0, (uint32_t)(b.x1 - b.x0 + 1), (uint32_t)(b.z1 - b.z0 + 1)};
+            R[(size_t)i * n_maps + m] = r;
+            max_cells[i] = std::max<uint64_t>(max_cells[i], (uint64_t)r.w * r.h);
+        }
+    }
+    SHF_CUDA(cudaMemcpyAsync(bf->rects.p, R, n_rects * sizeof(shf::BiomeRect), cudaMemcpyHostToDevice, s));
+    SHF_CUDA(cudaEventRecord(bf->rects_free, s));
+    tls_h2d += n_rects * sizeof(shf::BiomeRect);
+    // ---- the grids, leaf to root: one launch per layer over all maps ----
+    uint64_t jit_cells = 0;
+    for (uint32_t i = 0; i + 1u < L; i++) {
+        if (max_cells[i] == 0ull) continue;
+        if (max_cells[i] > 0xFFFFFFFFull) return fail(SHF_ERR_UNSUPPORTED, "cells per layer grid < 2^32", "map too large");
+        SHF_CUDA(bf->grid[i].ensure((size_t)max_cells[i] * n_maps * 2));
+    }
+    for (uint32_t i = 0; i < L; i++)
+        if (max_cells[i] && bf->layers[i].kind == SHF_LAYER_VORONOI) jit_cells = std::max(jit_cells, max_cells[bf->layers[i].parent]);
+    if (jit_cells) SHF_CUDA(bf->jitter.ensure((size_t)jit_cells * 2u * 3u * 8u * n_maps));
+    const shf::BiomeRect* rd = bf->rects.as<shf::BiomeRect>();
+    for (uint32_t i = 0; i < L; i++) {
+        if (max_cells[i] == 0ull) continue;   // not reachable from the root
+        const shf_biome_layer& ly = bf->layers[i];
+        const bool root = i + 1u == L;
+        shf::BiomeLaunch p{};
+        p.kind = ly.kind;
+        p.seed = bf->seeds[i];
+        p.voronoi_seed = bf->voronoi_seed;
+        p.ids = bf->ids;
+        p.n_maps = n_maps;
+        p.out_map_stride = root ? map_stride : max_cells[i];
+        p.out_row_stride = root ? row_stride : 0u;
+        const uint32_t par = ly.kind == SHF_LAYER_CONTINENT ? i : ly.parent;
+        p.in_map_stride = max_cells[par];
+        const uint64_t jit_stride = max_cells[par] * 2u * 3u;
+        if (ly.kind == SHF_LAYER_VORONOI) {
+            const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((max_cells[par] * 2u + 255u) / 256u, (uint64_t)bf->sm_count * 8u));
+            shf::voronoi_jitter_kernel<<<dim3(gx, n_maps), 256, 0, s>>>(bf->voronoi_seed, n_maps, rd + (size_t)par * n_maps,
+                                                                       jit_stride, bf->jitter.as<double>());
+            tls_launches++;
+        }
+        const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((max_cells[i] + 255u) / 256u, (uint64_t)bf->sm_count * 8u));
+        shf::biome_layer_kernel<<<dim3(gx, n_maps), 256, 0, s>>>(
+            p, rd + (size_t)i * n_maps, rd + (size_t)par * n_maps, bf->grid[par].as<uint16_t>(), bf->jitter.as<double>(),
+            jit_stride, root ? biomemap_dev : bf->grid[i].as<uint16_t>());
+        tls_launches++;
+        SHF_CUDA(cudaGetLastError());
+    }
     return SHF_OK;
 }
 

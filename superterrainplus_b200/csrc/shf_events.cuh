@@ -251,9 +251,12 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     if (y < g.H) events_row<K>(g, n, y, lane, colmask, cvt, dict, dict_stride, pool, pool_cap, counter, rowinfo, rowtotal,
                                stage_all[warp], tab_all[warp], mstage_all[warp]);
     // ---- last CTA of the chunk: first-bin index of every row ----
-    __threadfence();
+    // (one fence by the thread that signals, after the barrier that makes it see the CTA's writes: fences are cumulative)
     __syncthreads();
-    if (threadIdx.x == 0u) last_flag = atomicAdd(&sync[1u + n], 1u) == gridDim.x - 1u;
+    if (threadIdx.x == 0u) {
+        __threadfence();
+        last_flag = atomicAdd(&sync[1u + n], 1u) == gridDim.x - 1u;
+    }
     __syncthreads();
     if (!last_flag) return;
     __threadfence();

@@ -132,9 +132,12 @@ __global__ void __launch_bounds__(256) presence_kernel(const uint16_t* __restric
             if (bm[i]) atomicOr(&bitmap[(size_t)n * kDictWords + i], bm[i]);
     }
     // ---- the last CTA of the chunk: dictionary prefix ----
-    __threadfence();
+    // (one fence by the thread that signals, after the barrier that makes it see the CTA's writes: fences are cumulative)
     __syncthreads();
-    if (threadIdx.x == 0u) is_last = atomicAdd(&done[n], 1u) == gridDim.x - 1u;
+    if (threadIdx.x == 0u) {
+        __threadfence();
+        is_last = atomicAdd(&done[n], 1u) == gridDim.x - 1u;
+    }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -507,21 +510,30 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
 
 // Chain starts a row segment could not know (kTentative): the chain was alive when the segment began, so its start is
 // the one the segment above ended with for that value -- or, if that one is tentative as well, the one above it.
-__global__ void vpatch_kernel(Geo g, uint32_t nblk, uint32_t* __restrict__ cvt, const uint32_t* __restrict__ vexit) {
-    const uint32_t n = blockIdx.z, c = blockIdx.y;
+__global__ void __launch_bounds__(256) vpatch_kernel(Geo g, uint32_t nblk, uint32_t* __restrict__ cvt,
+                                                     const uint32_t* __restrict__ vexit) {
+    // CTA = 4 columns x 64 threads, a thread looks at 8 consecutive cells (two 16-byte loads; the first cell of segment
+    // 1 sits on a 128-byte line: cv_pad + 2r + 1 and the segment length are multiples of 32)
+    const uint32_t n = blockIdx.z, c = blockIdx.y * 4u + (threadIdx.x >> 6);
+    if (c >= g.PW) return;
     const uint32_t first = 1u + g.vseg_rows;                    // first output row of segment 1
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // cell = entering row of output row first + i
-    if (first + i >= g.H) return;
-    const uint32_t y = first + i;
-    const uint32_t seg = min((y - 1u) / g.vseg_rows, g.vseg - 1u);
-    uint32_t* cell = cvt + ((size_t)n * g.PW + c) * g.cv_pitch + g.cv_pad + y + 2u * g.r;
-    const uint32_t v = *cell;
-    if ((v >> 16) != kTentative) return;
-    const uint32_t id = v & 0xFFFFu, Bpad = g.Bpad;
-    uint32_t start = kTentative;
-    for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
-        start = vexit[((((size_t)n * (g.vseg - 1u) + k) * nblk + c / 32u) * Bpad + id) * 32u + (c & 31u)] >> 16;
-    *cell = id | (start << 16);
+    const uint32_t i0 = (blockIdx.x * 64u + (threadIdx.x & 63u)) * 8u;   // cell = entering row of output row first + i
+    if (first + i0 >= g.H) return;
+    uint32_t* cell0 = cvt + ((size_t)n * g.PW + c) * g.cv_pitch + g.cv_pad + first + i0 + 2u * g.r;
+    uint4 q[2] = {reinterpret_cast<const uint4*>(cell0)[0], reinterpret_cast<const uint4*>(cell0)[1]};   // (the pitch pads the column)
+    uint32_t v[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
+    const uint32_t Bpad = g.Bpad;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t y = first + i0 + (uint32_t)j;
+        if (y >= g.H || (v[j] >> 16) != kTentative) continue;
+        const uint32_t seg = min((y - 1u) / g.vseg_rows, g.vseg - 1u);
+        const uint32_t id = v[j] & 0xFFFFu;
+        uint32_t start = kTentative;
+        for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
+            start = vexit[((((size_t)n * (g.vseg - 1u) + k) * nblk + c / 32u) * Bpad + id) * 32u + (c & 31u)] >> 16;
+        cell0[j] = id | (start << 16);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ except Exception as e:
     print(" failed", e); print(open(sys.argv[1].replace(".json",".err")).read()[-800:])
 PY
 }
-for v in "--chunks 256" "--chunks 32" "--chunks 32 --dist blocky" "--dist blocky" "--workload C2 --min-seconds 0.3" "--workload C2 --dist blocky --min-seconds 0.3" "--workload C4 --min-seconds 0.3" "--workload C1 --min-seconds 0.3"; do
+for v in "--chunks 256" "--chunks 32" "--chunks 64" "--chunks 32 --dist blocky" "--dist blocky" "--workload C2 --min-seconds 0.3" "--workload C2 --dist blocky --min-seconds 0.3" "--workload C4 --min-seconds 0.3" "--workload C1 --min-seconds 0.3"; do
   name=$(echo $v | tr -d ' -.' )
   timeout 600 python bench.py $v --steps 20 --warmup 3 --no-cpu --no-e2e --no-consumer > gpurun_out/q_${tag}_${name}.json 2> gpurun_out/q_${tag}_${name}.err; echo "$v rc=$?"
   summ gpurun_out/q_${tag}_${name}.json

@@ -113,8 +113,8 @@ struct PinBuf {
 
 // measurement toggles, read once when the filter is created (never needed for correctness)
 struct shf_toggles {
-    bool no_speculation = false, no_cseg = false, no_vseg = false;
-    uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0;  // 0 = not set
+    bool no_speculation = false, no_cseg = false, no_vseg = false, no_persist = false;
+    uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0, debug_persist = 0;  // 0 = not set
 };
 
 struct shf_filter {
@@ -244,11 +244,25 @@ int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
     // sync: [0..1] the event counter (u64), [2] chunks finished, [3 + n] CTAs of chunk n finished, [3 + n_chunks + n]
     // presence CTAs of chunk n finished; all left at zero by their kernels
     uint32_t* sync = b->sync.as<uint32_t>();
-    shf::events_kernel<K><<<dim3((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks), shf::kEventWarps * 32, 0, s>>>(
-        g, b->colmask.as<uint32_t>(), b->cvt.as<uint32_t>(), b->dict.as<uint16_t>(), 32 * K,
-        b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), reinterpret_cast<unsigned long long*>(sync),
-        b->rowinfo.as<uint2>(), b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
-        b->chunktotal.as<unsigned long long>(), b->chunkbase.as<unsigned long long>(), b->hso.as<uint32_t>(), sync + 2);
+    const dim3 egrid((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks);
+    const bool fold = (uint64_t)egrid.x * egrid.y <= 4096ull;   // small calls: the scans ride on the last CTAs
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(sync);
+#define SHF_EVENTS_ARGS                                                                                                \
+    g, b->colmask.as<uint32_t>(), b->cvt.as<uint32_t>(), b->vexit.as<uint32_t>(), b->dict.as<uint16_t>(), 32 * K,       \
+        b->evpool.as<uint2>(), (unsigned long long)(b->evpool.cap / 8), counter, b->rowinfo.as<uint2>(),               \
+        b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(), b->chunktotal.as<unsigned long long>(),                 \
+        b->chunkbase.as<unsigned long long>(), b->hso.as<uint32_t>(), sync + 2
+    if (fold) {
+        shf::events_kernel<K, true><<<egrid, shf::kEventWarps * 32, 0, s>>>(SHF_EVENTS_ARGS);
+    } else {
+        shf::events_kernel<K, false><<<egrid, shf::kEventWarps * 32, 0, s>>>(SHF_EVENTS_ARGS);
+        shf::bases_kernel<<<g.n_chunks, 256, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+                                                     b->chunktotal.as<unsigned long long>(),
+                                                     b->chunkbase.as<unsigned long long>(), b->hso.as<uint32_t>(), counter,
+                                                     sync + 2);
+        tls_launches++;
+    }
+#undef SHF_EVENTS_ARGS
     tls_launches++;
     SHF_CUDA(cudaGetLastError());
     return SHF_OK;
@@ -283,13 +297,6 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
                                                                                 b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
                                                                                 b->vexit.as<uint32_t>());
         }
-        if (g.vseg > 1u) {
-            // chain starts the row segments could not know
-            const uint32_t rows = g.H - (1u + g.vseg_rows);
-            shf::vpatch_kernel<<<dim3((rows + 511u) / 512u, (g.PW + 3u) / 4u, g.n_chunks), 256, 0, s>>>(
-                g, nblk, b->cvt.as<uint32_t>(), b->vexit.as<uint32_t>());
-            tls_launches++;
-        }
         tls_launches++;
         SHF_CUDA(cudaGetLastError());
         SHF_CUDA(b->mark(2, s));
@@ -299,15 +306,23 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     Geo ge = g;
     ge.bins_cap = b->bins.cap / sizeof(shf_bin);
     ge.pool_cap = b->evpool.cap / 8;
-    const dim3 grid(g.T, g.n_chunks, g.cseg);
+    dim3 grid(g.T, g.n_chunks, g.cseg);
     const uint32_t threads = (g.TY + g.producers) * 32;
+    if (g.FW == 8u) SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (g.persist) {
+        // persistent CTAs: as many as are resident at once (g.persist = SMs of the device), each walking the tile list
+        int per_sm = 0;
+        if (g.FW == 8u) SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 8>, (int)threads, smem));
+        else SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 16>, (int)threads, smem));
+        const uint64_t resident = (uint64_t)std::max(per_sm, 1) * g.persist;
+        grid = dim3((uint32_t)std::min<uint64_t>(resident, (uint64_t)g.T * g.n_chunks), 1u, 1u);
+    }
     if (g.FW == 8u) {
-        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shf::emit_kernel<K, 8><<<grid, threads, smem, s>>>(
             ge, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
             b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
     } else {
-        SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shf::emit_kernel<K, 16><<<grid, threads, smem, s>>>(
             ge, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
             b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
@@ -721,6 +736,11 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
                 want--;
             }
         }
+        // large calls: persistent emit CTAs walking the flat tile list out of phase with each other (EmitItem)
+        g.persist = 0u;
+        if (!generic && g.cseg == 1u && W >= 64u && (uint64_t)n_chunks * g.T >= 4ull * (uint64_t)f->sm_count && !f->dbg.no_persist)
+            g.persist = (uint32_t)f->sm_count;
+        if (!generic && g.cseg == 1u && f->dbg.debug_persist) g.persist = f->dbg.debug_persist;   // tests: persistent CTAs on few "SMs"
         // vscan walks every column top to bottom, one warp per 32 columns: a small call (a single 1024x1024 chunk has 36
         // such warps) is split into up to eight row segments per block, each replaying the 2r+1 rows above its first
         g.vseg = 1u;
@@ -995,9 +1015,11 @@ int shf_filter_create(shf_filter** out, int device) {
     f->dbg.no_speculation = getenv("SHF_NO_SPECULATION") != nullptr;
     f->dbg.no_cseg = getenv("SHF_NO_CSEG") != nullptr;
     f->dbg.no_vseg = getenv("SHF_NO_VSEG") != nullptr;
+    f->dbg.no_persist = getenv("SHF_NO_PERSIST") != nullptr;
     f->dbg.debug_ty = env_u32("SHF_DEBUG_TY");
     f->dbg.debug_cseg = env_u32("SHF_DEBUG_CSEG");
     f->dbg.debug_vseg = env_u32("SHF_DEBUG_VSEG");
+    f->dbg.debug_persist = env_u32("SHF_DEBUG_PERSIST");
     *out = f;
     return SHF_OK;
 }

@@ -48,9 +48,24 @@ __device__ __forceinline__ void stage_masks(uint32_t* sdst, const uint32_t* __re
 
 // One pass over the row's presence masks. Writes at most `cap` records to `dst` (shared staging or the row's pool
 // slot); returns the number of events and adds the row's bins to `bins_total` (per-lane partial sums).
+// Chain start of a cell vscan_kernel wrote as kTentative: the cell entered in row segment `seg` >= 1 of the vertical scan
+// while its chain was alive since before that segment began, so the start is the one the segment above ended with for
+// that value -- or, if that one is tentative as well, the one above it (vexit = exit states of the segments).
+__device__ __forceinline__ uint32_t resolve_start(const Geo& g, const uint32_t* __restrict__ vexit_chunk, uint32_t c,
+                                                  uint32_t p, uint32_t id) {
+    const uint32_t yy = p - 2u * g.r;                                   // the output row at which the cell entered
+    const uint32_t seg = min((yy - 1u) / g.vseg_rows, g.vseg - 1u);
+    const uint32_t nblk = (g.PW + 31u) / 32u;
+    uint32_t start = kTentative;
+    for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
+        start = vexit_chunk[(((size_t)k * nblk + c / 32u) * g.Bpad + id) * 32u + (c & 31u)] >> 16;
+    return start;
+}
+
 template <int K>
 __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t lane, const uint32_t* __restrict__ cmask_row,
-                                             const uint32_t* __restrict__ cv, const uint32_t (&item)[K], uint16_t* tab, uint32_t* mstage, uint2* dst,
+                                             const uint32_t* __restrict__ cv, const uint32_t* __restrict__ vexit_chunk,
+                                             const uint32_t (&item)[K], uint16_t* tab, uint32_t* mstage, uint2* dst,
                                              uint32_t cap, uint32_t& bins_total) {
     const uint32_t PW = g.PW, span = g.span, two_r = 2u * g.r, W = g.W;
     int32_t last[K];
@@ -134,8 +149,14 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
                         if (o < span) cell[i] = colw[o];
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (o0 + lane + 32u * (uint32_t)i < span) tab[cell[i] & 0xFFFFu] = (uint16_t)(cell[i] >> 16);
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t o = o0 + lane + 32u * (uint32_t)i;
+                        if (o < span) {
+                            uint32_t start = cell[i] >> 16;
+                            if (start == kTentative) start = resolve_start(g, vexit_chunk, c, y + o, cell[i] & 0xFFFFu);
+                            tab[cell[i] & 0xFFFFu] = (uint16_t)start;
+                        }
+                    }
                 }
                 __syncwarp();
                 uint32_t vk[K];
@@ -200,7 +221,10 @@ __device__ __forceinline__ void events_row(const Geo& g, uint32_t n, uint32_t y,
                                            const uint16_t* __restrict__ dict, uint32_t dict_stride,
                                            uint2* __restrict__ pool, unsigned long long pool_cap,
                                            unsigned long long* __restrict__ counter, uint2* __restrict__ rowinfo,
-                                           uint32_t* __restrict__ rowtotal, uint2* stage, uint16_t* tab, uint32_t* mstage) {
+                                           uint32_t* __restrict__ rowtotal, const uint32_t* __restrict__ vexit,
+                                           uint2* stage, uint16_t* tab, uint32_t* mstage) {
+    // exit states of the vertical scan's row segments of this chunk (small calls only, g.vseg > 1)
+    const uint32_t* vexit_chunk = vexit + (size_t)n * (g.vseg - 1u) * ((g.PW + 31u) / 32u) * g.Bpad * 32u;
     const uint32_t* cmask_row = colmask + ((size_t)n * g.H + y) * ((g.PW + 31u) / 32u) * 32u * K;  // transposed masks
     const uint32_t* cv = cvt + (size_t)n * g.PW * g.cv_pitch;
     uint32_t item[K];
@@ -210,7 +234,7 @@ __device__ __forceinline__ void events_row(const Geo& g, uint32_t n, uint32_t y,
         item[k] = id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
     }
     uint32_t bins = 0u;
-    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cv, item, tab, mstage, stage, kEventStage, bins);
+    const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cv, vexit_chunk, item, tab, mstage, stage, kEventStage, bins);
     bins = __reduce_add_sync(kFull, bins);
     unsigned long long first = 0ull;
     if (lane == 0u) first = atomicAdd(counter, (unsigned long long)E);
@@ -225,18 +249,20 @@ __device__ __forceinline__ void events_row(const Geo& g, uint32_t n, uint32_t y,
         for (uint32_t i = lane; i < E; i += 32u) pool[first + i] = stage[i];
     } else {
         uint32_t again = 0u;
-        (void)walk_row<K>(g, y, lane, cmask_row, cv, item, tab, mstage, pool + first, E, again);
+        (void)walk_row<K>(g, y, lane, cmask_row, cv, vexit_chunk, item, tab, mstage, pool + first, E, again);
     }
 }
 
-// One warp per output row. The CTA that finishes a chunk last (sync[1 + n]) scans the chunk's bins per row into the
-// first-bin index of every row (rowbase), the chunk total and the closing offset entry; the CTA that finishes the last
-// chunk (sync[0]) scans the chunk totals into the first-bin index of every chunk and hands the event count to the host
-// (chunktotal[n_chunks]). Both re-arm their counters: a call needs neither a memset nor separate scan launches.
-template <int K>
+// One warp per output row.
+// FOLD (small calls, where every launch counts): the CTA that finishes a chunk last (sync[1 + n]) scans the chunk's bins
+// per row into the first-bin index of every row (rowbase), the chunk total and the closing offset entry; the CTA that
+// finishes the last chunk (sync[0]) scans the chunk totals into the first-bin index of every chunk and hands the event
+// count to the host (chunktotal[n_chunks]). Both re-arm their counters. Large calls leave that to bases_kernel: the
+// fence every CTA pays before it signals costs more there (+10 % on a 256-chunk batch) than the launch it saves.
+template <int K, bool FOLD>
 __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K == 4 ? 4 : 3)
     events_kernel(Geo g, const uint32_t* __restrict__ colmask, const uint32_t* __restrict__ cvt,
-                  const uint16_t* __restrict__ dict, uint32_t dict_stride,
+                  const uint32_t* __restrict__ vexit, const uint16_t* __restrict__ dict, uint32_t dict_stride,
                   uint2* __restrict__ pool, unsigned long long pool_cap, unsigned long long* __restrict__ counter,
                   uint2* __restrict__ rowinfo, uint32_t* __restrict__ rowtotal, uint32_t* __restrict__ rowbase,
                   unsigned long long* __restrict__ chunktotal, unsigned long long* __restrict__ chunkbase,
@@ -249,7 +275,8 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n = blockIdx.y, y = blockIdx.x * kEventWarps + warp;
     if (y < g.H) events_row<K>(g, n, y, lane, colmask, cvt, dict, dict_stride, pool, pool_cap, counter, rowinfo, rowtotal,
-                               stage_all[warp], tab_all[warp], mstage_all[warp]);
+                               vexit, stage_all[warp], tab_all[warp], mstage_all[warp]);
+    if (!FOLD) return;
     // ---- last CTA of the chunk: first-bin index of every row ----
     // (one fence by the thread that signals, after the barrier that makes it see the CTA's writes: fences are cumulative)
     __syncthreads();
@@ -278,6 +305,34 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     if (threadIdx.x == 0u) {
         chunkbase[g.n_chunks] = all;
         chunktotal[g.n_chunks] = *counter;   // records asked for by this call (read by the host)
+        *counter = 0ull;
+        sync[0] = 0u;
+    }
+}
+
+// The same scans for large calls, one CTA per chunk behind events_kernel<K, false>: rows of the chunk, then (the CTA that
+// finishes last) the chunks of the call.
+__global__ void __launch_bounds__(256) bases_kernel(Geo g, const uint32_t* __restrict__ rowtotal, uint32_t* __restrict__ rowbase,
+                                                    unsigned long long* __restrict__ chunktotal,
+                                                    unsigned long long* __restrict__ chunkbase, uint32_t* __restrict__ hso,
+                                                    unsigned long long* __restrict__ counter, uint32_t* __restrict__ sync) {
+    __shared__ unsigned long long warp_part[32];
+    __shared__ uint32_t last_flag;
+    const uint32_t n = blockIdx.x;
+    const unsigned long long total = cta_exclusive_scan(rowtotal + (size_t)n * g.H, rowbase + (size_t)n * g.H, g.H, warp_part);
+    if (threadIdx.x == 0u) {
+        chunktotal[n] = total;
+        hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)total;
+        __threadfence();
+        last_flag = atomicAdd(&sync[0], 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    const unsigned long long all = cta_exclusive_scan(chunktotal, chunkbase, g.n_chunks, warp_part);
+    if (threadIdx.x == 0u) {
+        chunkbase[g.n_chunks] = all;
+        chunktotal[g.n_chunks] = *counter;
         *counter = 0ull;
         sync[0] = 0u;
     }
@@ -399,6 +454,45 @@ __device__ __forceinline__ uint32_t staged_count(uint32_t row_addr, uint32_t id)
     return c;
 }
 
+// Work items of an emit CTA. An item = the pixels [X0, X1) of the TY rows of one row tile of one chunk.
+//  * one item per CTA (g.persist == 0): blockIdx = (tile, chunk, column segment), as planned on the host;
+//  * persistent CTAs (g.persist == 1, one or a few CTAs per SM, grid.x = G): CTA i takes the tiles i, i + G, i + 2G, ...
+//    of the flat tile list (static: every warp of the CTA derives the same sequence on its own, no hand-over). Its FIRST
+//    tile is cut at a column that grows with i -- pixels [cut, W) are emitted first, pixels [0, cut) last -- so that the
+//    CTAs of a launch run out of phase for its whole duration: a tile starts with 2r columns that only fill the window
+//    and write nothing, and CTAs marching in lockstep would all leave the HBM idle at the same moments (measured on a
+//    32-chunk batch: 7 waves x ~10 us of 790 us). Every CTA still does the same amount of work.
+struct EmitItem {
+    uint32_t n_chunk, tile, X0, X1;
+};
+__device__ __forceinline__ uint32_t emit_cut(const Geo& g) {   // first-tile cut of this CTA (a multiple of 16 pixels)
+    if (!g.persist || gridDim.x < 2u) return 0u;
+    return ((blockIdx.x * (g.W / 16u)) / gridDim.x) * 16u;
+}
+__device__ __forceinline__ uint32_t emit_item_count(const Geo& g) {
+    if (!g.persist) return 1u;
+    const uint32_t n_tiles = g.T * g.n_chunks;
+    return (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x + (emit_cut(g) ? 1u : 0u);
+}
+__device__ __forceinline__ EmitItem emit_item(const Geo& g, uint32_t k, uint32_t n_items) {
+    EmitItem it;
+    if (!g.persist) {
+        it.n_chunk = blockIdx.y;
+        it.tile = blockIdx.x;
+        it.X0 = blockIdx.z * g.cseg_px;
+        it.X1 = min(g.W, it.X0 + g.cseg_px);
+        return it;
+    }
+    const uint32_t cut = emit_cut(g);
+    const bool tail = cut && k + 1u == n_items;          // the rest of the first tile comes last
+    const uint32_t idx = blockIdx.x + (tail ? 0u : k) * gridDim.x;
+    it.n_chunk = idx / g.T;
+    it.tile = idx - it.n_chunk * g.T;
+    it.X0 = (k == 0u) ? cut : 0u;
+    it.X1 = tail ? cut : g.W;
+    return it;
+}
+
 // shared memory of an emit CTA:
 //   cring[TY][R][32K]  u8 / u16  vertical window counts (ring of R = 2r+1 + 16*stages columns per row), by compact id
 //   sbuf[TY][16][SS]   u16 / u32 horizontal window counts of the batch being emitted, SS bytes per pixel
@@ -416,19 +510,21 @@ __global__ void __launch_bounds__(640, 1)
     constexpr uint32_t SS = emit_sbuf_stride(K, FW);
     constexpr uint32_t ACAP = emit_act_cap(K);
     constexpr int SR = emit_acc_regs(K, FW);
-    // Column segments (blockIdx.z; small calls only): this CTA emits the pixels [X0, X1) of its rows. Its columns are
-    // the segment's own window span [X0, X1 + 2r): the first 2r of them only fill the window, exactly like the first 2r
-    // columns of a whole row; PW, column indices and ring slots below are local to the segment.
-    const uint32_t X0 = blockIdx.z * g.cseg_px, X1 = min(g.W, X0 + g.cseg_px);
-    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, PW = (X1 - X0) + two_r, stages = g.stages;
+    // An item (see EmitItem) emits the pixels [X0, X1) of its rows. Its columns are the item's own window span
+    // [X0, X1 + 2r): the first 2r of them only fill the window, exactly like the first 2r columns of a whole row; PW and
+    // column indices below are local to the item. Batches and ring slots are counted through all items of the CTA
+    // (gb0, ring0), so the barriers and the ring simply carry on from one item to the next: no CTA-wide barrier
+    // between items, the producers start on the next item while the consumers finish the current one.
+    const uint32_t TY = g.TY, R = g.R, span = g.span, two_r = 2u * g.r, stages = g.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t n_chunk = blockIdx.y, tile = blockIdx.x;
-    const uint32_t y0 = tile * TY;
     const uint32_t NP = g.producers;
-    // a call that runs ahead of the host's size checks must stay inside the buffers it was given (the host then sees the
-    // totals, grows the buffers and runs the call again)
-    if (chunkbase[n_chunk + 1u] > g.bins_cap) return;
-    const uint32_t n_batches = (PW + NB - 1u) / NB;
+    const uint32_t n_my_items = emit_item_count(g);
+    uint32_t total_batches = 0u;   // of all items of this CTA
+    for (uint32_t k = 0u; k < n_my_items; k++) {
+        const EmitItem it = emit_item(g, k, n_my_items);
+        total_batches += (it.X1 - it.X0 + two_r + NB - 1u) / NB;
+    }
+    uint32_t gb0 = 0u, ring0 = 0u;   // batches before the current item; ring slot of the current item's column 0
 
     uint8_t* cring = smem;
     uint8_t* sbuf_all = smem + (size_t)TY * R * CS;
@@ -441,7 +537,6 @@ __global__ void __launch_bounds__(640, 1)
         mbar_init(&empty_bar[threadIdx.x], TY);
     }
     __syncthreads();
-    const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
 
     if (warp >= TY) {
         // =============================== producer warps ===============================
@@ -453,10 +548,15 @@ __global__ void __launch_bounds__(640, 1)
         constexpr int PPB = NB / CPP;    // passes per batch
         constexpr int SW = CPP > 1 ? CPP / 2 : 1;  // 32-bit words of one row segment (one 16-bit sample when CPP = 1)
         const uint32_t part = lane % LPC, colq = lane / LPC;
-        const uint32_t tile_rows = min(TY, g.H - y0);
         const uint32_t bit0 = part * 128u;
         const uint32_t half = lane >> 4, lrow = lane & 15u;
         uint16_t* scr = reinterpret_cast<uint16_t*>(pscr_all) + (size_t)(warp - TY) * (2 * CPP * 16);
+        for (uint32_t item_k = 0u; item_k < n_my_items; item_k++) {
+        const EmitItem item = emit_item(g, item_k, n_my_items);
+        const uint32_t X0 = item.X0, PW = (item.X1 - item.X0) + two_r, n_chunk = item.n_chunk, tile = item.tile;
+        const uint32_t y0 = tile * TY, n_batches = (PW + NB - 1u) / NB;
+        const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
+        const uint32_t tile_rows = min(TY, g.H - y0);
         const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.P + X0;
         const uint8_t* base_tile = base + (((size_t)n_chunk * g.T + tile) * g.PW + X0) * CS + part * 16u;
         const uint32_t n_items = n_batches * PPB;
@@ -487,10 +587,10 @@ __global__ void __launch_bounds__(640, 1)
         if (t < n_items) fetch(t);
         for (; t < n_items; t += NP) {
             const uint32_t b = t / PPB, pass = t % PPB;
-            const uint32_t s = b % stages, cb = b * NB;
+            const uint32_t gb = gb0 + b, s = gb % stages, cb = b * NB;
             const uint32_t cu = pass * CPP + colq;
             const bool live = cb + cu < PW;
-            uint32_t slot = cb % R + cu;
+            uint32_t slot = (ring0 + cb) % R + cu;
             if (slot >= R) slot -= R;
             uint4 v = v_n;
             // transposed scratch: scr[half][column][row]
@@ -507,7 +607,7 @@ __global__ void __launch_bounds__(640, 1)
                 wa[0] = a0.x, wa[1] = a0.y, wa[2] = a0.z, wa[3] = a0.w, wa[4] = a1.x, wa[5] = a1.y, wa[6] = a1.z, wa[7] = a1.w;
                 wo[0] = o0.x, wo[1] = o0.y, wo[2] = o0.z, wo[3] = o0.w, wo[4] = o1.x, wo[5] = o1.y, wo[6] = o1.z, wo[7] = o1.w;
             }
-            if (b >= stages) mbar_wait(&empty_bar[s], (b / stages - 1u) & 1u);  // batch b - stages is consumed
+            if (gb >= stages) mbar_wait(&empty_bar[s], (gb / stages - 1u) & 1u);  // batch gb - stages is consumed
             uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -529,15 +629,24 @@ __global__ void __launch_bounds__(640, 1)
             __syncwarp();
             if (lane == 0u) mbar_arrive(&full_bar[s]);
         }
+        gb0 += n_batches;
+        ring0 = (ring0 + n_batches * NB) % R;
+        }
         return;
     }
 
     // =============================== consumer warps ===============================
-    const uint32_t y = y0 + warp;
-    const bool row_active = y < g.H;
     uint8_t* crow = cring + (size_t)warp * R * CS;
     uint8_t* sb = sbuf_all + (size_t)warp * NB * SS;
     uint2* act = act_all + (size_t)warp * ACAP;
+    for (uint32_t item_k = 0u; item_k < n_my_items; item_k++) {
+    const EmitItem item = emit_item(g, item_k, n_my_items);
+    const uint32_t X0 = item.X0, PW = (item.X1 - item.X0) + two_r, n_chunk = item.n_chunk;
+    const uint32_t n_batches = (PW + NB - 1u) / NB;
+    const uint32_t y = item.tile * TY + warp;
+    // a call that runs ahead of the host's size checks must stay inside the buffers it was given (the host then sees the
+    // totals, grows the buffers and runs the call again): such a chunk is walked through without output
+    const bool row_active = y < g.H && chunkbase[n_chunk + 1u] <= g.bins_cap;
     const uint2 ri = row_active ? rowinfo[(size_t)n_chunk * g.H + y] : make_uint2(0u, 0u);
     const uint2* ev = pool + ri.x;
     const uint32_t E = (unsigned long long)ri.x + ri.y <= g.pool_cap ? ri.y : 0u;
@@ -568,11 +677,11 @@ __global__ void __launch_bounds__(640, 1)
     bool clean = false;
     uint32_t pk_n = 0u, pk_slot = 0u, pk_entry = 0u;  // packed view (Ea <= 16): lane = slot * Ea + entry
 
-    uint32_t in_slot = 0u, out_slot = (R - span % R) % R;
+    uint32_t in_slot = ring0, out_slot = (ring0 + R - span % R) % R;
     for (uint32_t b = 0u; b < n_batches; b++) {
-        const uint32_t s = b % stages, cb = b * NB;
+        const uint32_t gb = gb0 + b, s = gb % stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
-        mbar_wait(&full_bar[s], (b / stages) & 1u);
+        mbar_wait(&full_bar[s], (gb / stages) & 1u);
         if (row_active) {
             // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
             if (cb >= span && ce - cb == (uint32_t)NB && in_slot + NB <= R && out_slot + NB <= R) {
@@ -766,7 +875,10 @@ __global__ void __launch_bounds__(640, 1)
             if (out_slot >= R) out_slot -= R;
         }
         __syncwarp();  // the batch's window counts and the ring columns it read are free again
-        if (b + stages < n_batches && lane == 0u) mbar_arrive(&empty_bar[s]);
+        if (gb + stages < total_batches && lane == 0u) mbar_arrive(&empty_bar[s]);
+    }
+    gb0 += n_batches;
+    ring0 = (ring0 + n_batches * NB) % R;
     }
 }
 

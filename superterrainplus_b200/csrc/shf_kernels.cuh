@@ -52,6 +52,7 @@ struct Geo {
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     uint32_t vseg, vseg_rows;      // vscan row segments per column block (1 = none) and output rows per segment (x32)
     uint32_t cseg, cseg_px;        // emit column segments per row tile (1 = none) and pixels per segment (x16)
+    uint32_t persist;              // emit CTAs are persistent and walk the flat tile list (large calls), see EmitItem
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
     unsigned long long bins_cap, pool_cap;  // capacities of the bin buffer / event pool (guards of a speculative call)
 };
@@ -390,8 +391,8 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     // Row segments (blockIdx.z; small calls only, see vseg in the plan): segment k > 0 starts at output row
     // Y = 1 + k * vseg_rows. It rebuilds the window state of row Y - 1 by replaying that window's 2r+1 rows -- the
     // counts come out exact, the chain starts cannot (a chain may have begun anywhere above): they are marked
-    // kTentative, travel into cvt as such while the chain lasts, and vpatch_kernel replaces them by the start the
-    // segment above ended with (its exit state, written below).
+    // kTentative, travel into cvt as such while the chain lasts, and events_kernel, the only reader, looks the few it
+    // needs up in the exit state of the segment above (written below; resolve_start in shf_events.cuh).
     const uint32_t seg = blockIdx.z, n_seg = g.vseg;
     const uint32_t y_first = seg == 0u ? 0u : 1u + seg * g.vseg_rows;
     const uint32_t y_end = seg + 1u < n_seg ? 1u + (seg + 1u) * g.vseg_rows : g.H;
@@ -508,34 +509,6 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
     }
 }
 
-// Chain starts a row segment could not know (kTentative): the chain was alive when the segment began, so its start is
-// the one the segment above ended with for that value -- or, if that one is tentative as well, the one above it.
-__global__ void __launch_bounds__(256) vpatch_kernel(Geo g, uint32_t nblk, uint32_t* __restrict__ cvt,
-                                                     const uint32_t* __restrict__ vexit) {
-    // CTA = 4 columns x 64 threads, a thread looks at 8 consecutive cells (two 16-byte loads; the first cell of segment
-    // 1 sits on a 128-byte line: cv_pad + 2r + 1 and the segment length are multiples of 32)
-    const uint32_t n = blockIdx.z, c = blockIdx.y * 4u + (threadIdx.x >> 6);
-    if (c >= g.PW) return;
-    const uint32_t first = 1u + g.vseg_rows;                    // first output row of segment 1
-    const uint32_t i0 = (blockIdx.x * 64u + (threadIdx.x & 63u)) * 8u;   // cell = entering row of output row first + i
-    if (first + i0 >= g.H) return;
-    uint32_t* cell0 = cvt + ((size_t)n * g.PW + c) * g.cv_pitch + g.cv_pad + first + i0 + 2u * g.r;
-    uint4 q[2] = {reinterpret_cast<const uint4*>(cell0)[0], reinterpret_cast<const uint4*>(cell0)[1]};   // (the pitch pads the column)
-    uint32_t v[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
-    const uint32_t Bpad = g.Bpad;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t y = first + i0 + (uint32_t)j;
-        if (y >= g.H || (v[j] >> 16) != kTentative) continue;
-        const uint32_t seg = min((y - 1u) / g.vseg_rows, g.vseg - 1u);
-        const uint32_t id = v[j] & 0xFFFFu;
-        uint32_t start = kTentative;
-        for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
-            start = vexit[((((size_t)n * (g.vseg - 1u) + k) * nblk + c / 32u) * Bpad + id) * 32u + (c & 31u)] >> 16;
-        cell0[j] = id | (start << 16);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // helpers of the emit kernel (shf_events.cuh): lane masks, shared-memory mbarriers
 // ------------------------------------------------------------------------------------------------------------------
@@ -645,34 +618,6 @@ __global__ void rowscan_kernel(Geo g, const uint32_t* __restrict__ rowtotal, uin
         chunktotal[n] = carry;
         hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)carry;
     }
-}
-
-// first-bin index of every chunk on the device (exclusive scan of the chunk totals; chunkbase[n_chunks] = all bins):
-// lets a repeated call launch its emit kernel without waiting for the host to see the totals
-__global__ void chunkbase_kernel(uint32_t n_chunks, const unsigned long long* __restrict__ chunktotal,
-                                 unsigned long long* __restrict__ chunkbase) {
-    __shared__ unsigned long long part[1024];
-    __shared__ unsigned long long carry;
-    const uint32_t t = threadIdx.x;
-    if (t == 0) carry = 0ull;
-    __syncthreads();
-    for (uint32_t i0 = 0u; i0 < n_chunks; i0 += blockDim.x) {
-        const uint32_t i = i0 + t;
-        const unsigned long long v = i < n_chunks ? chunktotal[i] : 0ull;
-        part[t] = v;
-        __syncthreads();
-        for (uint32_t off = 1u; off < blockDim.x; off <<= 1) {
-            const unsigned long long add = (t >= off) ? part[t - off] : 0ull;
-            __syncthreads();
-            part[t] += add;
-            __syncthreads();
-        }
-        if (i < n_chunks) chunkbase[i] = carry + part[t] - v;
-        __syncthreads();
-        if (t == blockDim.x - 1) carry += part[t];
-        __syncthreads();
-    }
-    if (t == 0) chunkbase[n_chunks] = carry;
 }
 
 }  // namespace shf

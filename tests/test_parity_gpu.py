@@ -267,6 +267,39 @@ def test_emit_column_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segm
         local.close()
 
 
+@pytest.mark.parametrize("w,h,r,biomes,kind,sms", [
+    (300, 70, 8, 6, "rare", 1), (520, 33, 16, 30, "stripes", 2), (260, 96, 32, 12, "blocky", 1), (200, 64, 64, 5, "iid", 3),
+    (640, 40, 16, 70, "iid", 2), (400, 50, 100, 3, "blocky", 1), (130, 90, 130, 9, "stripes", 2), (48, 100, 4, 2, "rare", 1),
+    (333, 57, 32, 100, "iid", 4), (17, 200, 6, 40, "iid", 1), (96, 96, 2, 200, "iid", 2),
+])
+def test_emit_persistent_ctas(shf, oracle_mod, w, h, r, biomes, kind, sms, monkeypatch):
+    """Large calls run the emitting kernel with persistent CTAs that walk the flat tile list, the first tile of every
+    CTA cut in two parts (emitted first and last) so that the CTAs run out of phase. Forced here on small batches with
+    the CTAs of 1-4 "SMs": several tiles per CTA, cuts at every multiple of 16, ragged last tiles, rings that wrap
+    between items; all chunks against the oracle, persistent and not."""
+    rng = np.random.default_rng(w * 31 + h * 977 + r)
+    nn = (2 * ((r + w - 1) // w) + 1, 2 * ((r + h - 1) // h) + 1)
+    maps = [random_map(rng, w, h, biomes, kind, nn) for _ in range(3)]
+    want = [oracle_mod.run_port(m, (w, h), nn, r) for m in maps]
+    monkeypatch.setenv("SHF_NO_CSEG", "1")
+    for setting in (str(sms), None):
+        if setting is None:
+            monkeypatch.delenv("SHF_DEBUG_PERSIST", raising=False)
+        else:
+            monkeypatch.setenv("SHF_DEBUG_PERSIST", setting)
+        local = shf.STPSingleHistogramFilter()
+        buf = shf.STPSingleHistogramFilter.STPFilterBuffer(0xFF)
+        hist = local.runBatch(maps, nn_info(shf, w, h, nn), buf, r)
+        base = buf.chunkBase()
+        per = w * h + 1
+        for i in range(3):
+            got = (hist.Bin["Item"][base[i]:base[i + 1]].copy(), hist.Bin["Weight"][base[i]:base[i + 1]].copy(),
+                   hist.HistogramStartOffset[i * per:(i + 1) * per].copy())
+            assert_same(got, want[i], f"{w}x{h} r={r} B={biomes} {kind} persistent={setting} chunk {i}")
+        buf.close()
+        local.close()
+
+
 def split_neighbours(m, w, h, nn):
     """The nn.x * nn.y chunk maps of a merged map, in local-index order (STPChunk::calcLocalChunkCoordinate)."""
     return [np.ascontiguousarray(m[cy * h:(cy + 1) * h, cx * w:(cx + 1) * w]) for cy in range(nn[1]) for cx in range(nn[0])]

@@ -418,6 +418,30 @@ def config4_chain(pkg, api, workloads, filt, local, stream, steps=8):
     return out
 
 
+def d2h_ceiling(barrier, sum_over_ranks, gib=2, reps=3):
+    """What the box can take: every rank copies `gib` GiB from its GPU into page-locked host memory with plain
+    cudaMemcpyAsync, all ranks at once (barrier before and after), `reps` times. Returns (this job's aggregate GB/s, the
+    slowest... per-rank GB/s). The end-to-end leg moves 34 GB of histograms per 256 chunks, so this is its ceiling."""
+    import torch
+
+    n = gib << 30
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt_local = time.perf_counter() - t0
+    barrier()
+    dt_all = time.perf_counter() - t0
+    total = sum_over_ranks(float(n * reps))
+    del src, dst
+    return total / dt_all / 1e9, n * reps / dt_local / 1e9
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -443,6 +467,13 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda" if args.backend == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     def max_over_ranks(x):
         if world == 1:
@@ -646,6 +677,11 @@ def run_ours(args):
         for b_ in bufs:
             b_.close()
         del host
+        # the same box, the same moment: what plain concurrent D2H copies into page-locked memory reach
+        ceil_all, ceil_rank = d2h_ceiling(barrier, sum_over_ranks)
+        e2e["d2h_ceiling_gb_per_s"] = ceil_all
+        e2e["d2h_ceiling_gb_per_s_this_rank_alone_share"] = ceil_rank
+        e2e["frac_of_d2h_ceiling"] = e2e["d2h_gb_per_s"] / ceil_all
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -103,6 +103,9 @@ namespace SuperTerrainPlus::STPAlgorithm {
 
 		~STPSingleHistogramFilter();
 
+		//the C handle of include/shf_b200.h behind this object (additive)
+		shf_filter* handle() noexcept { return this->Filter; }
+
 		//samplemap: host pointer, row-major, row stride nn_info.TotalMapSize.x, not retained.
 		//Synchronous; the result is also retrievable later with filter_buffer.readHistogram().
 		STPSingleHistogram operator()(const STPSample_t*, const STPNearestNeighbourInformation&, STPFilterBuffer&, unsigned int);

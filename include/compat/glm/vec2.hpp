@@ -16,4 +16,5 @@ namespace glm {
 	template<typename T> constexpr bool operator==(const tvec2<T>& a, const tvec2<T>& b) { return a.x == b.x && a.y == b.y; }
 	using uvec2 = tvec2<unsigned int>;
 	using vec2 = tvec2<float>;
+	using ivec2 = tvec2<int>;
 }

@@ -3,8 +3,10 @@
 # single-call configs. Usage: gpu_r2_quick.sh <tag> [pytest-filter]
 tag=${1:-q}
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -q -m gpu -x --timeout 1200 ${2:+-k "$2"} > gpurun_out/pytest_${tag}.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/pytest_${tag}.log
+for tf in tests/test_parity_gpu.py tests/test_heightfield_gpu.py tests/test_biome_gpu.py tests/test_fuzz_gpu.py tests/test_cpp_dropin.py; do
+  timeout 900 python -m pytest $tf -q -m gpu -x --timeout 200 --timeout-method=thread ${2:+-k "$2"} > gpurun_out/pytest_${tag}_$(basename $tf .py).log 2>&1; echo "pytest $tf rc=$?"
+  tail -4 gpurun_out/pytest_${tag}_$(basename $tf .py).log | cut -c1-400
+done
 summ() {
 python - "$1" <<'PY'
 import json,sys
@@ -18,13 +20,13 @@ PY
 }
 for v in "--chunks 256" "--chunks 32" "--chunks 64" "--chunks 32 --dist blocky" "--dist blocky" "--workload C2 --min-seconds 0.3" "--workload C2 --dist blocky --min-seconds 0.3" "--workload C4 --min-seconds 0.3" "--workload C1 --min-seconds 0.3"; do
   name=$(echo $v | tr -d ' -.' )
-  timeout 600 python bench.py $v --steps 20 --warmup 3 --no-cpu --no-e2e --no-consumer > gpurun_out/q_${tag}_${name}.json 2> gpurun_out/q_${tag}_${name}.err; echo "$v rc=$?"
+  timeout 240 python bench.py $v --steps 20 --warmup 3 --no-cpu --no-e2e --no-consumer > gpurun_out/q_${tag}_${name}.json 2> gpurun_out/q_${tag}_${name}.err; echo "$v rc=$?"
   summ gpurun_out/q_${tag}_${name}.json
 done
 KR='regex:emit_kernel|events_kernel|vscan_kernel|presence_kernel|remap_kernel|rowscan_kernel|vpatch|generic'
 for v in "--chunks 32" "--chunks 256"; do
   name=$(echo $v | tr -d ' -.' )
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 30 --csv --log-file gpurun_out/launches_${tag}_${name}.csv python bench.py $v --steps 2 --warmup 2 --no-cpu --no-e2e --no-consumer --parity-chunks 0 > gpurun_out/ncu_list_${tag}_${name}.log 2>&1; echo "ncu list $v rc=$?"
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 30 --csv --log-file gpurun_out/launches_${tag}_${name}.csv python bench.py $v --steps 2 --warmup 2 --no-cpu --no-e2e --no-consumer --parity-chunks 0 > gpurun_out/ncu_list_${tag}_${name}.log 2>&1; echo "ncu list $v rc=$?"
   python - gpurun_out/launches_${tag}_${name}.csv <<'PY'
 import csv,sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>10]

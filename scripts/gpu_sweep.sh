@@ -9,12 +9,12 @@ for dist in uniform blocky; do
 for r in 8 16 32 64 128; do
 for b in 4 16 64 256 1024; do
   chunks=32; if [ "$dist" = uniform ] && [ $b -ge 256 ]; then chunks=8; fi
-  timeout 300 python bench.py --workload C3 --dist $dist --radius $r --biomes $b --chunks $chunks --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/sw.json 2> gpurun_out/sw.err
+  timeout 300 python bench.py --workload C3 --dist $dist --radius $r --biomes $b --chunks $chunks --steps 5 --warmup 3 --no-cpu --no-e2e --no-consumer --parity-chunks 1 > gpurun_out/sw.json 2> gpurun_out/sw.err
   python - >> $out <<PY
 import json
 try:
     d=json.load(open("gpurun_out/sw.json"))
-    print("$dist r=$r B=$b chunks=$chunks | %.0f Mpx/s | step %.3f ms | emit %.3f | bins/px %.2f | K=%s TY=%s | step_frac %.3f" % (d["value"], d["ms_per_step"], d["phases_ms"]["emit"], d["config"]["bins_per_pixel"], d["config"]["plan"]["k_sets"], d["config"]["plan"]["rows_per_cta"], d["roofline"]["whole_step_frac"]))
+    print("$dist r=$r B=$b chunks=$chunks | %.0f Mpx/s | step %.3f ms | emit %.3f | bins/px %.2f | K=%s TY=%s | step_frac %.3f" % (d["value"], d["ms_per_step"], d["phases_ms"]["emit"], d["bins_per_pixel"], d["plan"]["k_sets"], d["plan"]["rows_per_cta"], d["roofline"]["whole_step_frac"]))
 except Exception as e:
     print("$dist r=$r B=$b | failed", e, open("gpurun_out/sw.err").read()[-300:].replace("\n"," "))
 PY

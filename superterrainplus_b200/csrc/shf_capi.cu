@@ -92,11 +92,12 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         size_t want = std::max(bytes, std::min(cap * 2, cap + (size_t(1) << 30)));
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        // (portable: page-locked for every CUDA context of the process, so that a caller may copy from it on any device)
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
         if (e != cudaSuccess && want != bytes) {
             (void)cudaGetLastError();
             want = bytes;
-            e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+            e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
         }
         cap = (e == cudaSuccess) ? want : 0;
         return e;
@@ -152,6 +153,8 @@ struct shf_buffer {
     unsigned char exec_type = SHF_EXEC_PARALLEL;
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;   // owned: carries finished ranges of a result to the host while the next is emitted
+    cudaEvent_t range_ev[8] = {};
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
         bins, hso, gstate, evpool, rowinfo, cvt, vexit, sync;
     PinBuf h_small, h_bins, h_hso;
@@ -214,6 +217,12 @@ struct shf_buffer {
         h_hso.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
+        for (cudaEvent_t& e : range_ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
     }
 };
 
@@ -306,7 +315,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     Geo ge = g;
     ge.bins_cap = b->bins.cap / sizeof(shf_bin);
     ge.pool_cap = b->evpool.cap / 8;
-    dim3 grid(g.T, g.n_chunks, g.cseg);
+    dim3 grid(g.T, g.emit_chunks, g.cseg);
     const uint32_t threads = (g.TY + g.producers) * 32;
     if (g.FW == 8u) SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else SHF_CUDA(cudaFuncSetAttribute(shf::emit_kernel<K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -316,7 +325,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         if (g.FW == 8u) SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 8>, (int)threads, smem));
         else SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 16>, (int)threads, smem));
         const uint64_t resident = (uint64_t)std::max(per_sm, 1) * g.persist;
-        grid = dim3((uint32_t)std::min<uint64_t>(resident, (uint64_t)g.T * g.n_chunks), 1u, 1u);
+        grid = dim3((uint32_t)std::min<uint64_t>(resident, (uint64_t)g.T * g.emit_chunks), 1u, 1u);
     }
     if (g.FW == 8u) {
         shf::emit_kernel<K, 8><<<grid, threads, smem, s>>>(
@@ -495,6 +504,43 @@ int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_d
     return publish(b, g);
 }
 
+// Emit + copy of a result that goes to the host (north_star: "result copies overlap compute via pinned async transfers
+// on per-GPU streams"): the chunks are emitted in up to four ranges; as soon as a range is done its bins and offsets start
+// towards the buffer's page-locked memory on a second stream while the next range is emitted. b->chunk_base is known
+// (the caller has seen the totals), the bin buffer is large enough.
+int emit_to_host(shf_buffer* b, Geo g, cudaStream_t s) {
+    const uint32_t n_chunks = g.n_chunks;
+    const size_t n_bins = (size_t)b->chunk_base[n_chunks];
+    const size_t per = (size_t)g.W * g.H + 1u;
+    SHF_CUDA(b->h_bins.ensure(std::max<size_t>(n_bins, 1) * sizeof(shf_bin)));
+    SHF_CUDA(b->h_hso.ensure((size_t)n_chunks * per * 4));
+    if (!b->copy_stream) SHF_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    const uint32_t n_ranges = std::min<uint32_t>(4u, n_chunks);
+    SHF_CUDA(b->mark(5, s));
+    for (uint32_t i = 0; i < n_ranges; i++) {
+        const uint32_t c0 = (uint32_t)((uint64_t)n_chunks * i / n_ranges), c1 = (uint32_t)((uint64_t)n_chunks * (i + 1u) / n_ranges);
+        g.emit_chunk0 = c0;
+        g.emit_chunks = c1 - c0;
+        const int st = dispatch_chain((int)g.K, b, g, s, 1);
+        if (st != SHF_OK) return st;
+        if (!b->range_ev[i]) SHF_CUDA(cudaEventCreateWithFlags(&b->range_ev[i], cudaEventDisableTiming));
+        SHF_CUDA(cudaEventRecord(b->range_ev[i], s));
+        SHF_CUDA(cudaStreamWaitEvent(b->copy_stream, b->range_ev[i], 0));
+        const size_t b0 = (size_t)b->chunk_base[c0], b1 = (size_t)b->chunk_base[c1];
+        if (b1 > b0) {
+            SHF_CUDA(cudaMemcpyAsync(b->h_bins.as<shf_bin>() + b0, b->bins.as<shf_bin>() + b0, (b1 - b0) * sizeof(shf_bin),
+                                     cudaMemcpyDeviceToHost, b->copy_stream));
+            tls_d2h += (b1 - b0) * sizeof(shf_bin);
+        }
+        SHF_CUDA(cudaMemcpyAsync(b->h_hso.as<uint32_t>() + c0 * per, b->hso.as<uint32_t>() + c0 * per, (c1 - c0) * per * 4,
+                                 cudaMemcpyDeviceToHost, b->copy_stream));
+        tls_d2h += (c1 - c0) * per * 4;
+    }
+    SHF_CUDA(b->mark(6, s));
+    SHF_CUDA(cudaStreamSynchronize(b->copy_stream));
+    return SHF_OK;
+}
+
 // A repeated call of the same shape on the same buffer (the pipeline's pooled buffers see chunk after chunk of one
 // geometry) runs the whole kernel sequence with the previous call's plan and buffer sizes and only then looks at the
 // numbers the checked path waits for twice (distinct values per chunk, bins per chunk, events): no host round trip
@@ -503,7 +549,7 @@ int run_generic(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_d
 // entry points, at the first query of the result for shf_run_device_async; when a check fails the result is discarded
 // and the checked path runs on the same input.
 int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* in_dev, bool vec8, uint32_t* h_nbiomes,
-                        uint64_t* h_totals, cudaStream_t s) {
+                        uint64_t* h_totals, cudaStream_t s, bool with_emit = true) {
     const uint32_t n_chunks = g.n_chunks;
     const int K = (int)g.K;
     b->ev_valid = false;
@@ -517,10 +563,12 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(3, s));
     SHF_CUDA(b->mark(4, s));
-    SHF_CUDA(b->mark(5, s));
-    st = dispatch_chain(K, b, g, s, 1);
-    if (st != SHF_OK) return st;
-    SHF_CUDA(b->mark(6, s));
+    if (with_emit) {
+        SHF_CUDA(b->mark(5, s));
+        st = dispatch_chain(K, b, g, s, 1);
+        if (st != SHF_OK) return st;
+        SHF_CUDA(b->mark(6, s));
+    }
     SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
     SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, s));
     tls_d2h += (size_t)n_chunks * 12 + 8;
@@ -533,17 +581,15 @@ void small_host_views(shf_buffer* b, uint32_t n_chunks, uint32_t** h_nbiomes, ui
     *h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
 }
 
-int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s);
+int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s, bool to_host = false);
+int result_to_host(shf_buffer* b, cudaStream_t s);
 
 // Completes a call enqueued by enqueue_speculative: waits for it, makes the checks the other path makes before it
 // launches and publishes the result -- or runs the checked path when the previous call's plan or buffer sizes did not
 // fit this input. SHF_OK without work when nothing is pending.
-int settle(shf_buffer* b) {
-    if (!b->deferred.active) return SHF_OK;
-    shf_buffer::Deferred d = b->deferred;
-    b->deferred.active = false;
-    SHF_CUDA(cudaEventSynchronize(b->done_ev));
-    const Geo& g = d.g;
+// the checks of a call that ran ahead with the plan in `g`: does the plan fit what the kernels found? On a hit
+// b->chunk_base and b->plan_biomes are set. emitted: the emitting kernel ran too (the bin buffer must have been large enough).
+bool speculation_holds(shf_buffer* b, const Geo& g, bool emitted) {
     const uint32_t n_chunks = g.n_chunks;
     uint32_t* h_nbiomes;
     uint64_t* h_totals;
@@ -558,24 +604,35 @@ int settle(shf_buffer* b) {
         hit = h_totals[i] <= 0xFFFFFFFFull;                                // (the checked path reports the overflow)
         total += h_totals[i];
     }
-    hit = hit && total <= b->bins.cap / sizeof(shf_bin);                   // bin buffer large enough
-    if (!hit) {
+    hit = hit && (!emitted || total <= b->bins.cap / sizeof(shf_bin));     // bin buffer large enough
+    if (!hit) return false;
+    b->chunk_base.assign(n_chunks + 1u, 0ull);
+    for (uint32_t i = 0; i < n_chunks; i++) b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
+    b->plan_biomes = bmax;
+    return true;
+}
+
+int settle(shf_buffer* b) {
+    if (!b->deferred.active) return SHF_OK;
+    shf_buffer::Deferred d = b->deferred;
+    b->deferred.active = false;
+    SHF_CUDA(cudaEventSynchronize(b->done_ev));
+    const Geo& g = d.g;
+    if (!speculation_holds(b, g, true)) {
         b->last_valid = false;
         b->spec_misses++;
         const int st = run_checked(&d.filt, b, g, d.in_dev, d.vec8, d.stream);
         if (st == SHF_OK) SHF_CUDA(cudaEventRecord(b->done_ev, d.stream));
         return st;
     }
-    b->chunk_base.assign(n_chunks + 1u, 0ull);
-    for (uint32_t i = 0; i < n_chunks; i++) b->chunk_base[i + 1u] = b->chunk_base[i] + h_totals[i];
-    b->plan_biomes = bmax;
     return publish(b, g);
 }
 
 // Run the whole kernel sequence. `in_dev` views the halo-extended region of every chunk in device memory.
 // deferred: return as soon as everything is enqueued when the call can run ahead (settle() completes it later).
 int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t in_chunk_stride, uint32_t in_row_stride,
-                  uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s, bool deferred = false) {
+                  uint32_t n_chunks, uint32_t W, uint32_t H, uint32_t r, cudaStream_t s, bool deferred = false,
+                  bool to_host = false) {
     Geo g{};
     g.W = W;
     g.H = H;
@@ -621,6 +678,32 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         Geo gs = b->last_g;
         gs.in_row_stride = in_row_stride;
         gs.in_chunk_stride = in_chunk_stride;
+        if (to_host) {
+            // the result goes to the host: run ahead up to the event lists, look at the totals (the page-locked output
+            // must be sized anyway), then emit in ranges whose copies overlap the next range's kernel
+            st = enqueue_speculative(f, b, gs, in_dev, vec8, h_nbiomes, h_totals, s, false);
+            if (st != SHF_OK) return st;
+            SHF_CUDA(cudaStreamSynchronize(s));
+            if (speculation_holds(b, gs, false)) {
+                SHF_CUDA(b->bins.ensure(std::max<size_t>((size_t)b->chunk_base[n_chunks], 1) * sizeof(shf_bin)));
+                st = emit_to_host(b, gs, s);
+                if (st != SHF_OK) return st;
+                SHF_CUDA(cudaEventRecord(b->done_ev, s));
+                b->done_recorded = true;
+                b->done_stream = s;
+                st = publish(b, gs);
+                b->on_host = true;
+                return st;
+            }
+            b->last_valid = false;
+            b->spec_misses++;
+            st = run_checked(f, b, g, in_dev, vec8, s, true);
+            if (st != SHF_OK) return st;
+            SHF_CUDA(cudaEventRecord(b->done_ev, s));
+            b->done_recorded = true;
+            b->done_stream = s;
+            return SHF_OK;
+        }
         st = enqueue_speculative(f, b, gs, in_dev, vec8, h_nbiomes, h_totals, s);
         if (st != SHF_OK) return st;
         SHF_CUDA(cudaEventRecord(b->done_ev, s));
@@ -634,7 +717,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         b->deferred.stream = s;
         return deferred ? SHF_OK : settle(b);
     }
-    st = run_checked(f, b, g, in_dev, vec8, s);
+    st = run_checked(f, b, g, in_dev, vec8, s, to_host);
     if (st != SHF_OK) return st;
     SHF_CUDA(cudaEventRecord(b->done_ev, s));
     b->done_recorded = true;
@@ -643,7 +726,7 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
 }
 
 // The checked path: two host round trips (distinct values per chunk -> plan; bins per chunk -> bin buffer).
-int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s) {
+int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s, bool to_host) {
     const uint32_t n_chunks = g.n_chunks, W = g.W, H = g.H, r = g.r;
     (void)r;
     uint32_t* h_nbiomes;
@@ -766,9 +849,12 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
     b->plan_k = generic ? 0u : (uint32_t)K;
     b->plan_ty = generic ? 1u : g.TY;
     b->plan_biomes = bmax;
+    g.emit_chunk0 = 0u;
+    g.emit_chunks = n_chunks;
     if (generic) {
         b->last_valid = false;
-        return run_generic(f, b, g, in_dev, vec8, bmax, h_totals, s);
+        const int st = run_generic(f, b, g, in_dev, vec8, bmax, h_totals, s);
+        return st == SHF_OK && to_host ? result_to_host(b, s) : st;
     }
 
     SHF_CUDA(b->base.ensure((size_t)n_chunks * g.T * g.PW * g.Bpad * g.FW / 8u));
@@ -790,13 +876,20 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
     if (st != SHF_OK) return st;
 
     // ---- emit ----
-    SHF_CUDA(b->mark(5, s));
-    st = dispatch_chain(K, b, g, s, 1);
-    if (st != SHF_OK) return st;
-    SHF_CUDA(b->mark(6, s));
+    if (to_host) {
+        st = emit_to_host(b, g, s);
+        if (st != SHF_OK) return st;
+    } else {
+        SHF_CUDA(b->mark(5, s));
+        st = dispatch_chain(K, b, g, s, 1);
+        if (st != SHF_OK) return st;
+        SHF_CUDA(b->mark(6, s));
+    }
     b->last_g = g;
     b->last_valid = true;
-    return publish(b, g);
+    st = publish(b, g);
+    b->on_host = to_host;
+    return st;
 }
 
 // (the calling entry point holds a DeviceGuard on f->device)
@@ -855,9 +948,7 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
                                    cudaMemcpyHostToDevice, s));
         tls_h2d += (size_t)PW * 2 * PH;
     }
-    st = run_on_device(f, b, b->din.as<uint16_t>(), cells, P, n_chunks, W, H, r, s);
-    if (st != SHF_OK) return st;
-    return to_host ? result_to_host(b, s) : SHF_OK;
+    return run_on_device(f, b, b->din.as<uint16_t>(), cells, P, n_chunks, W, H, r, s, false, to_host);
 }
 
 // Several concurrent operator() calls of the world pipeline served by one pass: the
@@ -968,9 +1059,8 @@ int run_neighbours(shf_filter* f, const uint16_t* const* chunk_maps, uint32_t n_
     st = gather_neighbours(f, b, chunk_maps, n_chunks, map_size, nn, radius, s);
     if (st != SHF_OK) return st;
     const uint32_t PW = map_size[0] + 2u * radius, PH = map_size[1] + 2u * radius, P = (PW + 7u) & ~7u;
-    st = run_on_device(f, b, b->din.as<uint16_t>(), (size_t)PH * P, P, n_chunks, map_size[0], map_size[1], radius, s);
-    if (st != SHF_OK) return st;
-    return to_host ? result_to_host(b, s) : SHF_OK;
+    return run_on_device(f, b, b->din.as<uint16_t>(), (size_t)PH * P, P, n_chunks, map_size[0], map_size[1], radius, s, false,
+                         to_host);
 }
 
 // the const accessors complete a call that is still waiting for its checks

@@ -471,13 +471,13 @@ __device__ __forceinline__ uint32_t emit_cut(const Geo& g) {   // first-tile cut
 }
 __device__ __forceinline__ uint32_t emit_item_count(const Geo& g) {
     if (!g.persist) return 1u;
-    const uint32_t n_tiles = g.T * g.n_chunks;
+    const uint32_t n_tiles = g.T * g.emit_chunks;
     return (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x + (emit_cut(g) ? 1u : 0u);
 }
 __device__ __forceinline__ EmitItem emit_item(const Geo& g, uint32_t k, uint32_t n_items) {
     EmitItem it;
     if (!g.persist) {
-        it.n_chunk = blockIdx.y;
+        it.n_chunk = g.emit_chunk0 + blockIdx.y;
         it.tile = blockIdx.x;
         it.X0 = blockIdx.z * g.cseg_px;
         it.X1 = min(g.W, it.X0 + g.cseg_px);
@@ -488,6 +488,7 @@ __device__ __forceinline__ EmitItem emit_item(const Geo& g, uint32_t k, uint32_t
     const uint32_t idx = blockIdx.x + (tail ? 0u : k) * gridDim.x;
     it.n_chunk = idx / g.T;
     it.tile = idx - it.n_chunk * g.T;
+    it.n_chunk += g.emit_chunk0;
     it.X0 = (k == 0u) ? cut : 0u;
     it.X1 = tail ? cut : g.W;
     return it;
@@ -583,7 +584,12 @@ __global__ void __launch_bounds__(640, 1)
             const uint32_t c = min(c0 + colq, PW - 1u);
             v_n = *reinterpret_cast<const uint4*>(base_tile + (size_t)c * CS);
         };
-        uint32_t t = warp - TY;
+        // Passes go to the producer warps round robin by their GLOBAL index (counted through all items of the CTA), not
+        // by their index inside the item: a warp's consecutive batches then stay NP / PPB <= stages apart. The parity
+        // wait below can only tell "the batch `stages` back is consumed" from "not yet"; a warp that jumped further
+        // ahead (items whose batch count is no multiple of the warp count would let it) would see the parity of an
+        // older phase, take it for its own and overwrite ring columns still in use.
+        uint32_t t = (warp - TY + NP - (gb0 * PPB) % NP) % NP;
         if (t < n_items) fetch(t);
         for (; t < n_items; t += NP) {
             const uint32_t b = t / PPB, pass = t % PPB;
@@ -607,7 +613,7 @@ __global__ void __launch_bounds__(640, 1)
                 wa[0] = a0.x, wa[1] = a0.y, wa[2] = a0.z, wa[3] = a0.w, wa[4] = a1.x, wa[5] = a1.y, wa[6] = a1.z, wa[7] = a1.w;
                 wo[0] = o0.x, wo[1] = o0.y, wo[2] = o0.z, wo[3] = o0.w, wo[4] = o1.x, wo[5] = o1.y, wo[6] = o1.z, wo[7] = o1.w;
             }
-            if (gb >= stages) mbar_wait(&empty_bar[s], (gb / stages - 1u) & 1u);  // batch gb - stages is consumed
+            if (gb >= stages) mbar_wait(&empty_bar[s], (gb / stages - 1u) & 1u, 0x10000000u | (item_k << 16) | gb);  // batch gb - stages is consumed
             uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -681,7 +687,7 @@ __global__ void __launch_bounds__(640, 1)
     for (uint32_t b = 0u; b < n_batches; b++) {
         const uint32_t gb = gb0 + b, s = gb % stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
-        mbar_wait(&full_bar[s], (gb / stages) & 1u);
+        mbar_wait(&full_bar[s], (gb / stages) & 1u, (item_k << 16) | gb);
         if (row_active) {
             // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
             if (cb >= span && ce - cb == (uint32_t)NB && in_slot + NB <= R && out_slot + NB <= R) {

@@ -26,6 +26,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
+#ifdef SHF_WATCHDOG
+#include <cstdio>
+#endif
 
 namespace shf {
 
@@ -53,6 +56,8 @@ struct Geo {
     uint32_t vseg, vseg_rows;      // vscan row segments per column block (1 = none) and output rows per segment (x32)
     uint32_t cseg, cseg_px;        // emit column segments per row tile (1 = none) and pixels per segment (x16)
     uint32_t persist;              // emit CTAs are persistent and walk the flat tile list (large calls), see EmitItem
+    uint32_t emit_chunk0, emit_chunks;   // the chunks one emit launch covers (a call whose result goes to the host emits
+                                         // in a few ranges, each copied while the next is computed)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495
     unsigned long long bins_cap, pool_cap;  // capacities of the bin buffer / event pool (guards of a speculative call)
 };
@@ -542,9 +547,20 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t sh) {
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));
     return r;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0u) {
     uint32_t done;
+#ifdef SHF_WATCHDOG   // debug builds: a wait that never ends reports itself and stops the kernel
+    unsigned long long spins = 0ull;
+#endif
+    (void)tag;
     do {
+#ifdef SHF_WATCHDOG
+        if (++spins == (1ull << 24)) {
+            if ((threadIdx.x & 31u) == 0u)
+                printf("mbar_wait stuck: block %u warp %u tag %u parity %u\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
+            __trap();
+        }
+#endif
         asm volatile(
             "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
             : "=r"(done)

@@ -171,3 +171,10 @@ void STPSingleHistogramFilter::filterDeviceAsync(const STPSample_t* const sample
 	check(shf_run_device_async(this->Filter, samplemap_device, chunk_stride, chunk_count, geo.MapSize, geo.Neighbour, geo.Total,
 		filter_buffer.Memory, radius, stream));
 }
+
+namespace SuperTerrainPlus::STPAlgorithm {
+	//the C handle behind a filter object, for the sibling classes that live on the same device (STPBiomeFactoryDevice)
+	shf_filter* STPFilterHandle(STPSingleHistogramFilter& filter) {
+		return filter.handle();
+	}
+}

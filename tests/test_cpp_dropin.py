@@ -48,3 +48,14 @@ def test_concurrent_callers_through_the_batcher(shf):
     assert run.returncode == 0, run.stdout + run.stderr
     assert "all batcher checks passed" in run.stdout
     print(run.stdout)
+
+
+@pytest.mark.gpu
+def test_device_biome_factory_feeds_the_filter_in_cpp(shf):
+    """SURVEY.md section 8 row f4 through the C++ classes: STPBiomeFactoryDevice produces the maps in device memory,
+    STPSingleHistogramFilter::filterDevice reads them in place; maps and histograms against the CPU restatements."""
+    shf.library()
+    build()
+    run = subprocess.run([os.path.join(HERE, "cpp", "test_biome")], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "all C++ biome factory checks passed" in run.stdout

@@ -114,8 +114,10 @@ struct PinBuf {
 
 // measurement toggles, read once when the filter is created (never needed for correctness)
 struct shf_toggles {
-    bool no_speculation = false, no_cseg = false, no_vseg = false, no_persist = false;
-    uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0, debug_persist = 0;  // 0 = not set
+    bool no_speculation = false, no_cseg = false, no_vseg = false;
+    uint32_t persist = 0;   // 1: persistent emit CTAs with the phase shift, 2: without
+    bool no_split = false;  // large calls: one emit launch instead of bulk + low-priority tail
+    uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0, debug_persist = 0, debug_np = 0, debug_extra = 0;  // 0 = not set
 };
 
 struct shf_filter {
@@ -154,6 +156,8 @@ struct shf_buffer {
     int device = -1;
     cudaStream_t stream = nullptr;  // owned, used by the host-pointer entry points
     cudaStream_t copy_stream = nullptr;   // owned: carries finished ranges of a result to the host while the next is emitted
+    cudaStream_t emit_stream = nullptr;   // owned, highest priority: the bulk of a large call's tiles (see launch_emit_split)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t range_ev[8] = {};
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
         bins, hso, gstate, evpool, rowinfo, cvt, vexit, sync;
@@ -219,6 +223,11 @@ struct shf_buffer {
         stream = nullptr;
         if (copy_stream) cudaStreamDestroy(copy_stream);
         copy_stream = nullptr;
+        if (emit_stream) cudaStreamDestroy(emit_stream);
+        emit_stream = nullptr;
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        ev_fork = ev_join = nullptr;
         for (cudaEvent_t& e : range_ev) {
             if (e) cudaEventDestroy(e);
             e = nullptr;
@@ -254,7 +263,7 @@ int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
     // presence CTAs of chunk n finished; all left at zero by their kernels
     uint32_t* sync = b->sync.as<uint32_t>();
     const dim3 egrid((g.H + shf::kEventWarps - 1) / shf::kEventWarps, g.n_chunks);
-    const bool fold = (uint64_t)egrid.x * egrid.y <= 4096ull;   // small calls: the scans ride on the last CTAs
+    const bool fold = (uint64_t)egrid.x * egrid.y <= 1024ull;   // small calls: the scans ride on the last CTAs
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(sync);
 #define SHF_EVENTS_ARGS                                                                                                \
     g, b->colmask.as<uint32_t>(), b->cvt.as<uint32_t>(), b->vexit.as<uint32_t>(), b->dict.as<uint16_t>(), 32 * K,       \
@@ -324,7 +333,7 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         int per_sm = 0;
         if (g.FW == 8u) SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 8>, (int)threads, smem));
         else SHF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shf::emit_kernel<K, 16>, (int)threads, smem));
-        const uint64_t resident = (uint64_t)std::max(per_sm, 1) * g.persist;
+        const uint64_t resident = (uint64_t)std::max(per_sm, 1) * (g.persist >> 1);
         grid = dim3((uint32_t)std::min<uint64_t>(resident, (uint64_t)g.T * g.emit_chunks), 1u, 1u);
     }
     if (g.FW == 8u) {
@@ -349,6 +358,49 @@ int dispatch_chain(int K, shf_buffer* b, const Geo& g, cudaStream_t s, int phase
         case 8: return launch_chain<8>(b, g, s, phase);
     }
     return fail(SHF_ERR_UNSUPPORTED, "K", "no kernel instance");
+}
+
+// Emit of a large call in two launches that run side by side: the bulk of the chunks as whole tiles on a stream of the
+// highest priority, the last few chunks cut into column segments (items a quarter or half as long) on the call's own
+// stream. Tiles are handed out dynamically, one CTA per SM, so a launch ends with the SMs finishing their last tile up to
+// a whole tile time apart (~85 us of a 32-chunk launch's 790 us were this tail and the start-up); the low-priority
+// launch's short items are only dispatched when no whole tile is waiting, i.e. into exactly those gaps.
+// (dense histograms only -- `bins_per_pixel` from this call's totals, or from the buffer's last result when the call runs
+// ahead of them: there the kernel waits for the HBM and the segments' extra window fill is free; sparse ones are bound by
+// instruction issue and lose what the fill costs: +5 % on a blocky 32-chunk batch.)
+int launch_emit_split(shf_filter* f, shf_buffer* b, const Geo& g, cudaStream_t s, double bins_per_pixel) {
+    const uint64_t tiles = (uint64_t)g.T * g.n_chunks;
+    uint32_t seg = 4u;
+    while (seg > 1u && (((g.W + seg - 1u) / seg + 15u) & ~15u) < std::max(64u, 2u * g.r)) seg--;
+    // enough short items to cover the drain of the bulk launch: about one tile per two SMs, in whole chunks
+    const uint32_t tail_chunks = (uint32_t)std::min<uint64_t>(g.n_chunks / 4u, ((uint64_t)f->sm_count / 2u + g.T - 1u) / g.T);
+    if (g.persist || g.cseg != 1u || seg < 2u || tail_chunks == 0u || tiles < 4ull * (uint64_t)f->sm_count || f->dbg.no_split ||
+        bins_per_pixel < 24.0)
+        return dispatch_chain((int)g.K, b, g, s, 1);
+    if (!b->emit_stream) {
+        int least = 0, greatest = 0;
+        SHF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SHF_CUDA(cudaStreamCreateWithPriority(&b->emit_stream, cudaStreamNonBlocking, greatest));
+        SHF_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        SHF_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    }
+    SHF_CUDA(cudaEventRecord(b->ev_fork, s));
+    SHF_CUDA(cudaStreamWaitEvent(b->emit_stream, b->ev_fork, 0));
+    Geo bulk = g;
+    bulk.emit_chunk0 = 0u;
+    bulk.emit_chunks = g.n_chunks - tail_chunks;
+    int st = dispatch_chain((int)g.K, b, bulk, b->emit_stream, 1);
+    if (st != SHF_OK) return st;
+    Geo tail = g;
+    tail.emit_chunk0 = g.n_chunks - tail_chunks;
+    tail.emit_chunks = tail_chunks;
+    tail.cseg_px = ((g.W + seg - 1u) / seg + 15u) & ~15u;
+    tail.cseg = (g.W + tail.cseg_px - 1u) / tail.cseg_px;
+    st = dispatch_chain((int)g.K, b, tail, s, 1);
+    if (st != SHF_OK) return st;
+    SHF_CUDA(cudaEventRecord(b->ev_join, b->emit_stream));
+    SHF_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
+    return SHF_OK;
 }
 
 // dictionary of every chunk: presence bitmap -> popcount prefix + number of distinct values (by the chunk's last CTA)
@@ -565,7 +617,9 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
     SHF_CUDA(b->mark(4, s));
     if (with_emit) {
         SHF_CUDA(b->mark(5, s));
-        st = dispatch_chain(K, b, g, s, 1);
+        // (density of the buffer's last result: the pipeline filters chunk after chunk of one world)
+        const double last_density = b->n_offsets ? (double)b->n_bins / (double)b->n_offsets : 0.0;
+        st = launch_emit_split(f, b, g, s, last_density);
         if (st != SHF_OK) return st;
         SHF_CUDA(b->mark(6, s));
     }
@@ -787,6 +841,7 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
         // small calls: 8 rows per CTA when 16 would leave more than half of the SMs idle (a single 512x512 chunk has 32
         // tiles of 16 rows: emit 0.054 -> 0.046 ms; a 2048x2048 chunk with its 128 tiles is better off with 16)
         // (8, not fewer: vscan dumps a base vector per tile and its fast variant wants multiples of 8)
+        if (f->dbg.debug_np) plan(std::min(f->dbg.debug_np, 4u), std::max(1u, f->dbg.debug_extra));  // measurements only
         if (f->dbg.debug_ty) ty = std::max(1u, std::min(ty, f->dbg.debug_ty));  // measurements only
         else if (ty > 8u && (uint64_t)n_chunks * ((H + ty - 1u) / ty) * 2u <= (uint64_t)f->sm_count) ty = 8u;
         if (smem_of(ty) > f->smem_optin) {
@@ -820,10 +875,13 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
             }
         }
         // large calls: persistent emit CTAs walking the flat tile list out of phase with each other (EmitItem)
+        // (opt-in: a static tile list per CTA measured 9 % slower on a 256-chunk batch than one CTA per tile, which the
+        // hardware hands out dynamically -- with or without the phase shift; kept for experiments, SHF_PERSIST=1)
         g.persist = 0u;
-        if (!generic && g.cseg == 1u && W >= 64u && (uint64_t)n_chunks * g.T >= 4ull * (uint64_t)f->sm_count && !f->dbg.no_persist)
-            g.persist = (uint32_t)f->sm_count;
-        if (!generic && g.cseg == 1u && f->dbg.debug_persist) g.persist = f->dbg.debug_persist;   // tests: persistent CTAs on few "SMs"
+        if (!generic && g.cseg == 1u && W >= 64u && (uint64_t)n_chunks * g.T >= 4ull * (uint64_t)f->sm_count && f->dbg.persist)
+            g.persist = 2u * (uint32_t)f->sm_count + (f->dbg.persist > 1u ? 0u : 1u);
+        // (g.persist = 2 * SMs to occupy + 1 if every CTA's first tile is cut in two; tests: persistent CTAs on few "SMs")
+        if (!generic && g.cseg == 1u && f->dbg.debug_persist) g.persist = 2u * f->dbg.debug_persist + 1u;
         // vscan walks every column top to bottom, one warp per 32 columns: a small call (a single 1024x1024 chunk has 36
         // such warps) is split into up to eight row segments per block, each replaying the 2r+1 rows above its first
         g.vseg = 1u;
@@ -881,7 +939,7 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
         if (st != SHF_OK) return st;
     } else {
         SHF_CUDA(b->mark(5, s));
-        st = dispatch_chain(K, b, g, s, 1);
+        st = launch_emit_split(f, b, g, s, (double)b->chunk_base[n_chunks] / ((double)n_chunks * W * H));
         if (st != SHF_OK) return st;
         SHF_CUDA(b->mark(6, s));
     }
@@ -1105,8 +1163,11 @@ int shf_filter_create(shf_filter** out, int device) {
     f->dbg.no_speculation = getenv("SHF_NO_SPECULATION") != nullptr;
     f->dbg.no_cseg = getenv("SHF_NO_CSEG") != nullptr;
     f->dbg.no_vseg = getenv("SHF_NO_VSEG") != nullptr;
-    f->dbg.no_persist = getenv("SHF_NO_PERSIST") != nullptr;
+    f->dbg.persist = env_u32("SHF_PERSIST");
+    f->dbg.no_split = getenv("SHF_NO_SPLIT") != nullptr;
     f->dbg.debug_ty = env_u32("SHF_DEBUG_TY");
+    f->dbg.debug_np = env_u32("SHF_DEBUG_NP");         // producer warps of an emit CTA
+    f->dbg.debug_extra = env_u32("SHF_DEBUG_EXTRA");   // ring batches beyond those in production
     f->dbg.debug_cseg = env_u32("SHF_DEBUG_CSEG");
     f->dbg.debug_vseg = env_u32("SHF_DEBUG_VSEG");
     f->dbg.debug_persist = env_u32("SHF_DEBUG_PERSIST");

@@ -48,13 +48,14 @@ __device__ __forceinline__ void stage_masks(uint32_t* sdst, const uint32_t* __re
 
 // One pass over the row's presence masks. Writes at most `cap` records to `dst` (shared staging or the row's pool
 // slot); returns the number of events and adds the row's bins to `bins_total` (per-lane partial sums).
-// Chain start of a cell vscan_kernel wrote as kTentative: the cell entered in row segment `seg` >= 1 of the vertical scan
-// while its chain was alive since before that segment began, so the start is the one the segment above ended with for
-// that value -- or, if that one is tentative as well, the one above it (vexit = exit states of the segments).
+// Chain start of a value whose cells in the window of output row y, column c were all written as kTentative by
+// vscan_kernel: they entered in row segments >= 1 of the vertical scan while the chain was alive since before those
+// segments began. The chain is the one the value had when the segment above row y's ended (every cell of the window had
+// entered by then or belongs to row y's own segment), so its start is what that segment ended with for the value -- or,
+// if that is tentative as well, what the one above it ended with (vexit = exit states of the segments).
 __device__ __forceinline__ uint32_t resolve_start(const Geo& g, const uint32_t* __restrict__ vexit_chunk, uint32_t c,
-                                                  uint32_t p, uint32_t id) {
-    const uint32_t yy = p - 2u * g.r;                                   // the output row at which the cell entered
-    const uint32_t seg = min((yy - 1u) / g.vseg_rows, g.vseg - 1u);
+                                                  uint32_t y, uint32_t id) {
+    const uint32_t seg = min((max(y, 1u) - 1u) / g.vseg_rows, g.vseg - 1u);
     const uint32_t nblk = (g.PW + 31u) / 32u;
     uint32_t start = kTentative;
     for (int k = (int)seg - 1; k >= 0 && start == kTentative; k--)
@@ -141,6 +142,11 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
                 // chain start of its value (all cells of one value inside a window agree)
                 // (2r+1 <= 511 on this path: two rounds of 8 cells per lane; the loads of a round go out before its stores)
                 const uint32_t* colw = cv + (size_t)c * g.cv_pitch + g.cv_pad + y;  // the column's window, contiguous
+                if (g.vseg > 1u) {   // (cells may carry tentative starts: a value keeps 0xFFFF unless a cell knows better)
+#pragma unroll
+                    for (int k = 0; k < K; k++) tab[k * 32 + lane] = (uint16_t)kTentative;
+                    __syncwarp();
+                }
                 for (uint32_t o0 = 0u; o0 < span; o0 += 256u) {
                     uint32_t cell[8];
 #pragma unroll
@@ -151,17 +157,16 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const uint32_t o = o0 + lane + 32u * (uint32_t)i;
-                        if (o < span) {
-                            uint32_t start = cell[i] >> 16;
-                            if (start == kTentative) start = resolve_start(g, vexit_chunk, c, y + o, cell[i] & 0xFFFFu);
-                            tab[cell[i] & 0xFFFFu] = (uint16_t)start;
-                        }
+                        if (o < span && (cell[i] >> 16) != kTentative) tab[cell[i] & 0xFFFFu] = (uint16_t)(cell[i] >> 16);
                     }
                 }
                 __syncwarp();
                 uint32_t vk[K];
 #pragma unroll
-                for (int k = 0; k < K; k++) vk[k] = mem[k] ? (uint32_t)tab[k * 32 + lane] : 0u;
+                for (int k = 0; k < K; k++) {
+                    vk[k] = mem[k] ? (uint32_t)tab[k * 32 + lane] : 0u;
+                    if (mem[k] && vk[k] == kTentative) vk[k] = resolve_start(g, vexit_chunk, c, y, (uint32_t)(k * 32) + lane);
+                }
 #pragma unroll
                 for (int kk = 0; kk < K; kk++) {
                     unsigned m2 = mb[kk];
@@ -466,7 +471,7 @@ struct EmitItem {
     uint32_t n_chunk, tile, X0, X1;
 };
 __device__ __forceinline__ uint32_t emit_cut(const Geo& g) {   // first-tile cut of this CTA (a multiple of 16 pixels)
-    if (!g.persist || gridDim.x < 2u) return 0u;
+    if (!(g.persist & 1u) || gridDim.x < 2u) return 0u;
     return ((blockIdx.x * (g.W / 16u)) / gridDim.x) * 16u;
 }
 __device__ __forceinline__ uint32_t emit_item_count(const Geo& g) {
@@ -499,8 +504,10 @@ __device__ __forceinline__ EmitItem emit_item(const Geo& g, uint32_t k, uint32_t
 //   sbuf[TY][16][SS]   u16 / u32 horizontal window counts of the batch being emitted, SS bytes per pixel
 //   act[TY][32K+32]    8 B  the events overlapping the pixels being emitted, in list order
 
+// (K = 1 is compiled for 768 threads, i.e. at most 80 registers: its small-call plans (8 rows + 4 producer warps = 384
+// threads, < 76 KB of shared memory) then fit two CTAs per SM; at 86 registers a single 1024 x 1024 chunk lost 38 %)
 template <int K, int FW>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(K == 1 ? 768 : 640, 1)
     emit_kernel(Geo g, const uint16_t* __restrict__ cmap, const uint8_t* __restrict__ base,
                 const uint2* __restrict__ pool, const uint2* __restrict__ rowinfo, const uint32_t* __restrict__ rowbase,
                 const uint64_t* __restrict__ chunkbase, uint2* __restrict__ bins, uint32_t* __restrict__ hso) {

@@ -55,7 +55,8 @@ struct Geo {
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]
     uint32_t vseg, vseg_rows;      // vscan row segments per column block (1 = none) and output rows per segment (x32)
     uint32_t cseg, cseg_px;        // emit column segments per row tile (1 = none) and pixels per segment (x16)
-    uint32_t persist;              // emit CTAs are persistent and walk the flat tile list (large calls), see EmitItem
+    uint32_t persist;              // != 0: emit CTAs are persistent and walk the flat tile list (large calls), see
+                                   // EmitItem; = 2 * SMs to occupy + (1 if the first tile of every CTA is cut in two)
     uint32_t emit_chunk0, emit_chunks;   // the chunks one emit launch covers (a call whose result goes to the host emits
                                          // in a few ranges, each copied while the next is computed)
     float inv_total;               // 1.0f / float((2r+1)^2), SHF.cpp:495

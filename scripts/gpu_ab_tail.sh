@@ -1,0 +1,21 @@
+#!/bin/bash
+mkdir -p gpurun_out
+line() { python - "$1" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1]))
+    print("   step %.4f ms | emit %.4f | remap_vscan %.4f events %.4f" % (d["ms_per_step"], d["phases_ms"]["emit"], d["phases_ms"]["remap_vscan"], d["phases_ms"]["events"]))
+except Exception as e:
+    print("   failed", e, open("gpurun_out/ab.err").read()[-300:])
+PY
+}
+for mode in "X=1" "SHF_DEBUG_TAIL=2" "SHF_DEBUG_TAIL=4" "SHF_DEBUG_TAIL=6" "SHF_DEBUG_TAIL=8" "SHF_DEBUG_TAIL=3 SHF_DEBUG_TAILSEG=2" "SHF_DEBUG_TAIL=6 SHF_DEBUG_TAILSEG=2" "SHF_DEBUG_TY=8 SHF_DEBUG_NP=2 SHF_DEBUG_EXTRA=1" "SHF_DEBUG_TY=8 SHF_DEBUG_NP=2 SHF_DEBUG_EXTRA=1 SHF_NO_SPLIT=1" "SHF_DEBUG_TY=8 SHF_DEBUG_NP=2 SHF_DEBUG_EXTRA=1 SHF_DEBUG_TAIL=2"; do
+  echo "== 32 chunks [$mode]"
+  env $mode timeout 240 python bench.py --chunks 32 --steps 30 --warmup 3 --no-cpu --no-e2e --no-consumer --parity-chunks 0 > gpurun_out/ab.json 2> gpurun_out/ab.err
+  line gpurun_out/ab.json
+done
+for mode in "X=1" "SHF_DEBUG_TAIL=6" "SHF_DEBUG_TAIL=12"; do
+  echo "== 256 chunks [$mode]"
+  env $mode timeout 240 python bench.py --chunks 256 --steps 20 --warmup 3 --no-cpu --no-e2e --no-consumer --parity-chunks 0 > gpurun_out/ab.json 2> gpurun_out/ab.err
+  line gpurun_out/ab.json
+done

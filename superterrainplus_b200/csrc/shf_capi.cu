@@ -117,6 +117,8 @@ struct shf_toggles {
     bool no_speculation = false, no_cseg = false, no_vseg = false;
     uint32_t persist = 0;   // 1: persistent emit CTAs with the phase shift, 2: without
     bool no_split = false;  // large calls: one emit launch instead of bulk + low-priority tail
+    bool no_small_ids = false;  // always build the dictionary and the remapped copy
+    uint32_t debug_tail = 0, debug_tailseg = 0;
     uint32_t debug_ty = 0, debug_cseg = 0, debug_vseg = 0, debug_persist = 0, debug_np = 0, debug_extra = 0;  // 0 = not set
 };
 
@@ -158,6 +160,8 @@ struct shf_buffer {
     cudaStream_t copy_stream = nullptr;   // owned: carries finished ranges of a result to the host while the next is emitted
     cudaStream_t emit_stream = nullptr;   // owned, highest priority: the bulk of a large call's tiles (see launch_emit_split)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_stream = nullptr;    // owned: work of a call that is off its critical path (the dictionary of a call
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;   // that reads the caller's sample values as compact ids)
     cudaEvent_t range_ev[8] = {};
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
         bins, hso, gstate, evpool, rowinfo, cvt, vexit, sync;
@@ -186,6 +190,7 @@ struct shf_buffer {
     cudaStream_t done_stream = nullptr;
     bool done_recorded = false;
     uint64_t spec_misses = 0;           // calls that ran ahead with a plan that did not fit and were repeated
+    const uint16_t* ids = nullptr;      // where the current call's kernels read compact ids: cmap, or the caller's maps
     cudaEvent_t ev[kEvRing][kPhases + 1] = {};
     uint64_t ev_calls = 0;   // profiled calls so far; call c uses ring slot c % kEvRing
     bool ev_valid = false;
@@ -228,6 +233,11 @@ struct shf_buffer {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         ev_fork = ev_join = nullptr;
+        if (aux_stream) cudaStreamDestroy(aux_stream);
+        aux_stream = nullptr;
+        if (ev_aux_fork) cudaEventDestroy(ev_aux_fork);
+        if (ev_aux_join) cudaEventDestroy(ev_aux_join);
+        ev_aux_fork = ev_aux_join = nullptr;
         for (cudaEvent_t& e : range_ev) {
             if (e) cudaEventDestroy(e);
             e = nullptr;
@@ -306,12 +316,12 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
         if (g.vseg > 1u) SHF_CUDA(b->vexit.ensure((size_t)g.n_chunks * (g.vseg - 1u) * nblk * 32 * K * 32 * 4));
         if (g.TY % 8u == 0u) {
             SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-            shf::vscan_kernel<K, true><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
+            shf::vscan_kernel<K, true><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->ids, b->cvt.as<uint32_t>(),
                                                                                b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
                                                                                b->vexit.as<uint32_t>());
         } else {
             SHF_CUDA(cudaFuncSetAttribute(shf::vscan_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-            shf::vscan_kernel<K, false><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->cmap.as<uint16_t>(), b->cvt.as<uint32_t>(),
+            shf::vscan_kernel<K, false><<<vgrid, shf::kVscanThreads, vsmem, s>>>(g, b->ids, b->cvt.as<uint32_t>(),
                                                                                 b->base.as<uint8_t>(), b->colmask.as<uint32_t>(),
                                                                                 b->vexit.as<uint32_t>());
         }
@@ -338,11 +348,11 @@ int launch_chain(shf_buffer* b, const Geo& g, cudaStream_t s, int phase) {
     }
     if (g.FW == 8u) {
         shf::emit_kernel<K, 8><<<grid, threads, smem, s>>>(
-            ge, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+            ge, b->ids, b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
             b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
     } else {
         shf::emit_kernel<K, 16><<<grid, threads, smem, s>>>(
-            ge, b->cmap.as<uint16_t>(), b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
+            ge, b->ids, b->base.as<uint8_t>(), b->evpool.as<uint2>(), b->rowinfo.as<uint2>(),
             b->rowbase.as<uint32_t>(), b->chunkbase.as<uint64_t>(), b->bins.as<uint2>(), b->hso.as<uint32_t>());
     }
     tls_launches++;
@@ -370,10 +380,11 @@ int dispatch_chain(int K, shf_buffer* b, const Geo& g, cudaStream_t s, int phase
 // instruction issue and lose what the fill costs: +5 % on a blocky 32-chunk batch.)
 int launch_emit_split(shf_filter* f, shf_buffer* b, const Geo& g, cudaStream_t s, double bins_per_pixel) {
     const uint64_t tiles = (uint64_t)g.T * g.n_chunks;
-    uint32_t seg = 4u;
+    uint32_t seg = f->dbg.debug_tailseg ? f->dbg.debug_tailseg : 4u;
     while (seg > 1u && (((g.W + seg - 1u) / seg + 15u) & ~15u) < std::max(64u, 2u * g.r)) seg--;
     // enough short items to cover the drain of the bulk launch: about one tile per two SMs, in whole chunks
-    const uint32_t tail_chunks = (uint32_t)std::min<uint64_t>(g.n_chunks / 4u, ((uint64_t)f->sm_count / 2u + g.T - 1u) / g.T);
+    uint32_t tail_chunks = (uint32_t)std::min<uint64_t>(g.n_chunks / 4u, ((uint64_t)f->sm_count / 2u + g.T - 1u) / g.T);
+    if (f->dbg.debug_tail) tail_chunks = std::min(f->dbg.debug_tail, g.n_chunks - 1u);   // measurements only
     if (g.persist || g.cseg != 1u || seg < 2u || tail_chunks == 0u || tiles < 4ull * (uint64_t)f->sm_count || f->dbg.no_split ||
         bins_per_pixel < 24.0)
         return dispatch_chain((int)g.K, b, g, s, 1);
@@ -442,6 +453,11 @@ int prepare_common(shf_filter* f, shf_buffer* b, const Geo& g, const uint16_t* i
     SHF_CUDA(b->chunktotal.ensure((size_t)(g.n_chunks + 1) * 8));  // + the event counter
     SHF_CUDA(b->chunkbase.ensure((size_t)(g.n_chunks + 1) * 8));
     SHF_CUDA(b->hso.ensure((size_t)g.n_chunks * ((size_t)g.W * g.H + 1u) * 4));
+    if (g.small_ids) {   // the sample values are the compact ids: the kernels read the caller's maps in place
+        b->ids = in_dev;
+        return SHF_OK;
+    }
+    b->ids = b->cmap.as<uint16_t>();
     const dim3 pgrid(shf_rows_grid(g.PH, g.n_chunks, f->sm_count), g.n_chunks);
     if (vec8)
         shf::remap_kernel<8><<<pgrid, 256, 0, s>>>(in_dev, g, b->bitmap.as<uint32_t>(), b->prefix.as<uint32_t>(),
@@ -606,8 +622,25 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
     const int K = (int)g.K;
     b->ev_valid = false;
     SHF_CUDA(b->mark(0, s));
-    int st = launch_dictionary(f, b, g, in_dev, vec8, s);
-    if (st != SHF_OK) return st;
+    int st;
+    const bool side_dictionary = g.small_ids != 0u;   // (its phase then reads ~0 in the profile: it is off the stream)
+    if (side_dictionary) {
+        // nothing downstream reads the dictionary when the sample values are the ids: it only has to confirm that they
+        // still are (distinct values, largest value), so it runs beside the scan instead of in front of it
+        if (!b->aux_stream) {
+            SHF_CUDA(cudaStreamCreateWithFlags(&b->aux_stream, cudaStreamNonBlocking));
+            SHF_CUDA(cudaEventCreateWithFlags(&b->ev_aux_fork, cudaEventDisableTiming));
+            SHF_CUDA(cudaEventCreateWithFlags(&b->ev_aux_join, cudaEventDisableTiming));
+        }
+        SHF_CUDA(cudaEventRecord(b->ev_aux_fork, s));
+        SHF_CUDA(cudaStreamWaitEvent(b->aux_stream, b->ev_aux_fork, 0));
+        st = launch_dictionary(f, b, g, in_dev, vec8, b->aux_stream);
+        if (st != SHF_OK) return st;
+        SHF_CUDA(cudaEventRecord(b->ev_aux_join, b->aux_stream));
+    } else {
+        st = launch_dictionary(f, b, g, in_dev, vec8, s);
+        if (st != SHF_OK) return st;
+    }
     SHF_CUDA(b->mark(1, s));
     st = prepare_common(f, b, g, in_dev, vec8, s);
     if (st != SHF_OK) return st;
@@ -623,16 +656,17 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
         if (st != SHF_OK) return st;
         SHF_CUDA(b->mark(6, s));
     }
-    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
+    if (side_dictionary) SHF_CUDA(cudaStreamWaitEvent(s, b->ev_aux_join, 0));
+    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
     SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, s));
-    tls_d2h += (size_t)n_chunks * 12 + 8;
+    tls_d2h += (size_t)n_chunks * 16 + 8;
     return SHF_OK;
 }
 
-// page-locked scratch of a call: distinct values per chunk (u32) and bins per chunk + event count (u64)
+// page-locked scratch of a call: distinct values and largest value per chunk (2 x u32), bins per chunk + event count (u64)
 void small_host_views(shf_buffer* b, uint32_t n_chunks, uint32_t** h_nbiomes, uint64_t** h_totals) {
     *h_nbiomes = b->h_small.as<uint32_t>();
-    *h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 4 + 15) & ~size_t(15)));
+    *h_totals = reinterpret_cast<uint64_t*>(b->h_small.as<uint8_t>() + (((size_t)n_chunks * 8 + 15) & ~size_t(15)));
 }
 
 int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, bool vec8, cudaStream_t s, bool to_host = false);
@@ -648,10 +682,14 @@ bool speculation_holds(shf_buffer* b, const Geo& g, bool emitted) {
     uint32_t* h_nbiomes;
     uint64_t* h_totals;
     small_host_views(b, n_chunks, &h_nbiomes, &h_totals);
-    uint32_t bmax = 0;
-    for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
+    uint32_t bmax = 0, vmax = 0;
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        bmax = std::max(bmax, h_nbiomes[i]);
+        vmax = std::max(vmax, h_nbiomes[n_chunks + i]);
+    }
     const uint32_t need_k = bmax <= 32u ? 1u : bmax <= 64u ? 2u : bmax <= 128u ? 4u : 8u;
     bool hit = bmax <= 256u && need_k == g.K;                              // else another plan (or the wide path) is due
+    hit = hit && (!g.small_ids || vmax < 32u * g.K);                       // sample values still usable as compact ids
     hit = hit && h_totals[n_chunks] <= b->evpool.cap / 8;                  // event pool large enough
     uint64_t total = 0;
     for (uint32_t i = 0; i < n_chunks && hit; i++) {
@@ -710,14 +748,14 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     b->has_result = false;
     if (!b->done_ev) SHF_CUDA(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
     if (b->done_recorded && b->done_stream != s) SHF_CUDA(cudaStreamWaitEvent(s, b->done_ev, 0));
-    if ((size_t)n_chunks * 16 + 64 > b->h_small.cap && b->done_recorded)
+    if ((size_t)n_chunks * 24 + 64 > b->h_small.cap && b->done_recorded)
         SHF_CUDA(cudaEventSynchronize(b->done_ev));  // (a copy into the old page-locked block may be in flight)
 
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));
-    SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 4));
+    SHF_CUDA(b->nbiomes.ensure((size_t)n_chunks * 8));
     SHF_CUDA(b->sync.ensure_zeroed(((size_t)n_chunks * 2 + 4) * 4, s));   // arrival counters, left at zero by their kernels
-    SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 16 + 64));
+    SHF_CUDA(b->h_small.ensure((size_t)n_chunks * 24 + 64));
     uint32_t* h_nbiomes;
     uint64_t* h_totals;
     small_host_views(b, n_chunks, &h_nbiomes, &h_totals);
@@ -732,6 +770,11 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
         Geo gs = b->last_g;
         gs.in_row_stride = in_row_stride;
         gs.in_chunk_stride = in_chunk_stride;
+        if (gs.small_ids && !(vec8 && in_row_stride >= gs.PW + 32u)) {   // this view cannot be read in place
+            gs.small_ids = 0u;
+        }
+        gs.ids_row_stride = gs.small_ids ? in_row_stride : gs.P;
+        gs.ids_chunk_stride = gs.small_ids ? in_chunk_stride : (uint64_t)gs.PH * gs.P;
         if (to_host) {
             // the result goes to the host: run ahead up to the event lists, look at the totals (the page-locked output
             // must be sized anyway), then emit in ranges whose copies overlap the next range's kernel
@@ -794,11 +837,14 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
         if (st != SHF_OK) return st;
     }
     SHF_CUDA(b->mark(1, s));
-    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, s));
-    tls_d2h += (size_t)n_chunks * 4;
+    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
+    tls_d2h += (size_t)n_chunks * 8;
     SHF_CUDA(cudaStreamSynchronize(s));
-    uint32_t bmax = 0;
-    for (uint32_t i = 0; i < n_chunks; i++) bmax = std::max(bmax, h_nbiomes[i]);
+    uint32_t bmax = 0, vmax = 0;
+    for (uint32_t i = 0; i < n_chunks; i++) {
+        bmax = std::max(bmax, h_nbiomes[i]);
+        vmax = std::max(vmax, h_nbiomes[n_chunks + i]);
+    }
     if (bmax > 65535u) return fail(SHF_ERR_UNSUPPORTED, "distinct samples per chunk <= 65535", "compact ids are 16 bits wide");
     const int K = bmax <= 32u ? 1 : bmax <= 64u ? 2 : bmax <= 128u ? 4 : 8;
     g.K = K;
@@ -904,6 +950,12 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
             }
         }
     }
+    // Sample values that are small numbers (biome ids counted from 0, as the demo's registry does) serve as compact ids
+    // themselves when that costs no wider plan: no remapped copy, the kernels read the caller's maps where they lie
+    // (16-byte aligned rows with room for the producers' whole-segment loads behind the halo).
+    g.small_ids = !generic && vec8 && vmax < 32u * (uint32_t)K && g.in_row_stride >= g.PW + 32u && !f->dbg.no_small_ids;
+    g.ids_row_stride = g.small_ids ? g.in_row_stride : g.P;
+    g.ids_chunk_stride = g.small_ids ? g.in_chunk_stride : (uint64_t)g.PH * g.P;
     b->plan_k = generic ? 0u : (uint32_t)K;
     b->plan_ty = generic ? 1u : g.TY;
     b->plan_biomes = bmax;
@@ -989,7 +1041,8 @@ int run_host(shf_filter* f, const uint16_t* const* maps, uint32_t n_chunks, cons
     st = bind_device(f, b);
     if (st != SHF_OK) return st;
     const uint32_t W = map_size[0], H = map_size[1], r = radius;
-    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 7u) & ~7u;
+    // (row pitch of the device copy: 16-byte rows with 32 samples of slack, so that the kernels can read it in place)
+    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 39u) & ~7u;
     const size_t sx = (size_t)W * (nn[0] / 2u), sy = (size_t)H * (nn[1] / 2u);
     const size_t S = total[0];
     if (S < sx + W + r) return fail(SHF_ERR_INVALID_ARGUMENT, "TotalMapSize.x >= start + W + r", "row stride too small");
@@ -1074,7 +1127,7 @@ int run_multi(shf_filter* f, const uint16_t* const* maps, shf_buffer* const* buf
 int gather_neighbours(shf_filter* f, shf_buffer* b, const uint16_t* const* chunk_maps, uint32_t n_chunks,
                       const uint32_t map_size[2], const uint32_t nn[2], uint32_t radius, cudaStream_t s) {
     const uint32_t W = map_size[0], H = map_size[1], r = radius;
-    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 7u) & ~7u;
+    const uint32_t PW = W + 2u * r, PH = H + 2u * r, P = (PW + 39u) & ~7u;
     const size_t x0 = (size_t)W * (nn[0] / 2u) - r, y0 = (size_t)H * (nn[1] / 2u) - r;  // halo origin in the merged map
     const size_t cells = (size_t)PH * P;
     const uint32_t per = nn[0] * nn[1];
@@ -1116,7 +1169,7 @@ int run_neighbours(shf_filter* f, const uint16_t* const* chunk_maps, uint32_t n_
     cudaStream_t s = to_host ? b->stream : user_stream;
     st = gather_neighbours(f, b, chunk_maps, n_chunks, map_size, nn, radius, s);
     if (st != SHF_OK) return st;
-    const uint32_t PW = map_size[0] + 2u * radius, PH = map_size[1] + 2u * radius, P = (PW + 7u) & ~7u;
+    const uint32_t PW = map_size[0] + 2u * radius, PH = map_size[1] + 2u * radius, P = (PW + 39u) & ~7u;
     return run_on_device(f, b, b->din.as<uint16_t>(), (size_t)PH * P, P, n_chunks, map_size[0], map_size[1], radius, s, false,
                          to_host);
 }
@@ -1165,7 +1218,10 @@ int shf_filter_create(shf_filter** out, int device) {
     f->dbg.no_vseg = getenv("SHF_NO_VSEG") != nullptr;
     f->dbg.persist = env_u32("SHF_PERSIST");
     f->dbg.no_split = getenv("SHF_NO_SPLIT") != nullptr;
+    f->dbg.no_small_ids = getenv("SHF_NO_SMALL_IDS") != nullptr;
     f->dbg.debug_ty = env_u32("SHF_DEBUG_TY");
+    f->dbg.debug_tail = env_u32("SHF_DEBUG_TAIL");
+    f->dbg.debug_tailseg = env_u32("SHF_DEBUG_TAILSEG");
     f->dbg.debug_np = env_u32("SHF_DEBUG_NP");         // producer warps of an emit CTA
     f->dbg.debug_extra = env_u32("SHF_DEBUG_EXTRA");   // ring batches beyond those in production
     f->dbg.debug_cseg = env_u32("SHF_DEBUG_CSEG");

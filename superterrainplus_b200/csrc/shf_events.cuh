@@ -236,7 +236,7 @@ __device__ __forceinline__ void events_row(const Geo& g, uint32_t n, uint32_t y,
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const uint32_t id = k * 32 + lane;
-        item[k] = id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
+        item[k] = g.small_ids ? id : id < dict_stride ? (uint32_t)dict[(size_t)n * dict_stride + id] : 0u;
     }
     uint32_t bins = 0u;
     const uint32_t E = walk_row<K>(g, y, lane, cmask_row, cv, vexit_chunk, item, tab, mstage, stage, kEventStage, bins);
@@ -563,9 +563,9 @@ __global__ void __launch_bounds__(K == 1 ? 768 : 640, 1)
         const EmitItem item = emit_item(g, item_k, n_my_items);
         const uint32_t X0 = item.X0, PW = (item.X1 - item.X0) + two_r, n_chunk = item.n_chunk, tile = item.tile;
         const uint32_t y0 = tile * TY, n_batches = (PW + NB - 1u) / NB;
-        const uint16_t* cm = cmap + (size_t)n_chunk * g.PH * g.P;
+        const uint16_t* cm = cmap + (size_t)n_chunk * g.ids_chunk_stride;
         const uint32_t tile_rows = min(TY, g.H - y0);
-        const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.P + X0;
+        const uint16_t* seg_row = cm + (size_t)min(half ? y0 + lrow : y0 + lrow + span, g.PH - 1u) * g.ids_row_stride + X0;
         const uint8_t* base_tile = base + (((size_t)n_chunk * g.T + tile) * g.PW + X0) * CS + part * 16u;
         const uint32_t n_items = n_batches * PPB;
         uint32_t seg_n[SW];

@@ -42,6 +42,10 @@ struct Geo {
     uint32_t W, H, r, span;        // chunk map size, radius, 2r+1
     uint32_t PW, PH;               // W+2r, H+2r : the halo-extended region
     uint32_t P;                    // row pitch (elements) of cmap / vstart
+    uint32_t small_ids;            // the sample values themselves serve as compact ids (all < 32K): no remap pass, the
+                                   // kernels read the caller's maps in place
+    uint32_t ids_row_stride;       // where vscan / emit read compact ids: cmap (P, PH * P) or the input view
+    uint64_t ids_chunk_stride;
     uint32_t n_chunks;
     uint32_t in_row_stride;        // input view: sample(n,p,c) = in[n*in_chunk_stride + p*in_row_stride + c]
     uint64_t in_chunk_stride;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) presence_kernel(const uint16_t* __restric
                                                        uint32_t* __restrict__ done) {
     __shared__ uint32_t bm[kDictWords];
     __shared__ uint32_t part[256];
-    __shared__ uint32_t is_last;
+    __shared__ uint32_t is_last, top_value;
     const uint32_t n = blockIdx.y;
     for (int i = threadIdx.x; i < kDictWords; i += blockDim.x) bm[i] = 0u;
     __syncthreads();
@@ -150,14 +154,18 @@ __global__ void __launch_bounds__(256) presence_kernel(const uint16_t* __restric
     __threadfence();
     const uint32_t t = threadIdx.x;
     const uint32_t* words = bitmap + (size_t)n * kDictWords;
-    uint32_t local[8], sum = 0u;
+    uint32_t local[8], sum = 0u, top = 0u;
+    if (t == 0u) top_value = 0u;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         local[i] = sum;
-        sum += __popc(__ldcg(words + t * 8 + i));   // (other CTAs' atomics: read past the L1)
+        const uint32_t w = __ldcg(words + t * 8 + i);   // (other CTAs' atomics: read past the L1)
+        sum += __popc(w);
+        if (w) top = (t * 8u + (uint32_t)i) * 32u + 31u - (uint32_t)__clz((int)w);
     }
     part[t] = sum;
     __syncthreads();
+    if (top) atomicMax(&top_value, top);
     for (int off = 1; off < 256; off <<= 1) {   // Hillis-Steele over the 256 partial sums
         const uint32_t v = (t >= (uint32_t)off) ? part[t - off] : 0u;
         __syncthreads();
@@ -167,7 +175,10 @@ __global__ void __launch_bounds__(256) presence_kernel(const uint16_t* __restric
     const uint32_t excl = part[t] - sum;
 #pragma unroll
     for (int i = 0; i < 8; i++) prefix[(size_t)n * kDictWords + t * 8 + i] = excl + local[i];
-    if (t == 255u) n_biomes[n] = part[255];
+    if (t == 255u) {
+        n_biomes[n] = part[255];
+        n_biomes[gridDim.y + n] = top_value;   // largest sample value of the chunk (the scan's barriers order the atomicMax)
+    }
     if (t == 0u) done[n] = 0u;
 }
 
@@ -383,8 +394,11 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
 #pragma unroll
     for (int k = 0; k < K; k++) vs.tm[k * 32 + lane] = 0u;
     __syncwarp();
-    const size_t P = g.P;
-    const uint16_t* in = cmap + (size_t)n * g.PH * P + c;      // row p (entering)
+    const size_t P = g.ids_row_stride;
+    // (ids are clamped into the state table: only a call running ahead with a plan that does not fit its input -- its
+    // result is discarded -- can meet larger ones, when it reads the caller's raw samples as ids)
+    const uint32_t id_max = (uint32_t)Bpad - 1u;
+    const uint16_t* in = cmap + (size_t)n * g.ids_chunk_stride + c;      // row p (entering)
     uint32_t ci = g.cv_pad;   // index of row p in the column-major map: cv_pad + p (the 8-row groups start on a line)
     const uint32_t nblk = gridDim.x;
     uint32_t* mout = tmask + ((size_t)n * g.H * nblk + blockIdx.x) * Bpad;   // row y
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         for (; p + 8u <= two_r + 1u; p += 8u) {
             uint32_t s_in[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) s_in[j] = in[j * P];
+            for (int j = 0; j < 8; j++) s_in[j] = min((uint32_t)in[j * P], id_max);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 vs.push(ci, s_in[j] | (vs.enter(s_in[j], p + j) << 16));
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             in += 8 * P;
         }
         for (; p <= two_r; p++) {
-            const uint32_t sv = *in;
+            const uint32_t sv = min((uint32_t)*in, id_max);
             vs.push(ci, sv | (vs.enter(sv, p) << 16));
             if ((++ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
             in += P;
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         // ---- replay of the window of output row y_first - 1: rows y_first - 1 .. y_first + 2r - 1 ----
         in += (size_t)(y_first - 1u) * P;
         for (uint32_t q = 0u; q <= two_r; q++) {
-            vs.enter_tentative(*in);
+            vs.enter_tentative(min((uint32_t)*in, id_max));
             in += P;
         }
         ci = g.cv_pad + y_first + two_r;                       // a multiple of 32 by construction
@@ -443,7 +457,7 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
 
     // ---- output rows 1 .. H-1: row y + 2r enters, row y - 1 leaves ----
     uint32_t y = seg == 0u ? 1u : y_first;
-    const uint16_t* out = cmap + (size_t)n * g.PH * P + c + (size_t)(y - 1u) * P;     // row y - 1 (leaving)
+    const uint16_t* out = cmap + (size_t)n * g.ids_chunk_stride + c + (size_t)(y - 1u) * P;     // row y - 1 (leaving)
     // groups of 8 rows; the samples of a group are loaded while the group before it is processed (one DRAM round trip
     // hidden per group). With TY a multiple of 8 a tile's first row is always the last row of a group (ALIGNED); other
     // plans check every row.
@@ -460,8 +474,8 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
             uint32_t s_in[8], s_out[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                s_in[j] = n_in[j];
-                s_out[j] = n_out[j];
+                s_in[j] = min(n_in[j], id_max);
+                s_out[j] = min(n_out[j], id_max);
             }
             if (y + 16u <= y_end) {
 #pragma unroll
@@ -493,8 +507,8 @@ __global__ void __launch_bounds__(kVscanThreads) vscan_kernel(Geo g, const uint1
         }
     }
     for (; y < y_end; y++) {
-        const uint32_t sv = *in;
-        vs.push(ci, sv | (vs.step(sv, *out, two_r + y) << 16));
+        const uint32_t sv = min((uint32_t)*in, id_max);
+        vs.push(ci, sv | (vs.step(sv, min((uint32_t)*out, id_max), two_r + y) << 16));
         if ((++ci & (kVscanStageRows - 1u)) == 0u) vs.flush(ci - kVscanStageRows);
         vs.store_mask(mout);
         in += P;

@@ -20,6 +20,7 @@ namespace shf {
 constexpr int kEventWarps = 4;          // rows per CTA of events_kernel
 constexpr uint32_t kEventStage = 192;   // events of one row staged in shared memory before their pool slot is known
 constexpr uint32_t kNoEvent = 0xFFFFFFFFu;
+constexpr int32_t kNeverSeen = -0x40000000;   // "last column" of a value not met yet: further back than any window
 
 // Event record, 8 bytes: x = compact id | sample value << 16, y = first pixel | (last pixel + 1) << 16
 // 32-column mask blocks staged per cp.async group (two groups = 4 KB in flight per warp)
@@ -73,7 +74,7 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
     uint32_t open[K], openxb[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        last[k] = -1;
+        last[k] = kNeverSeen;
         open[k] = kNoEvent;
         openxb[k] = 0u;
     }
@@ -98,6 +99,21 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
         uint32_t rem[K];  // lane = compact id 32k + lane, bit j = column c0 + j
 #pragma unroll
         for (int k = 0; k < K; k++) rem[k] = mstage[(gi & 1u) * GW + (wi * K + k) * 32u + lane];
+        if (span >= 32u) {
+            // Most words hold no birth at all (on dense maps every value is present in every column: nothing is born
+            // after column 0): when no lane's first column in the word opens a chain -- with 2r+1 >= 32 no later one
+            // of the word can either -- the chains just carry on to their last column in the word.
+            uint32_t noisy = 0u;   // (branch-free: ffs(0) = 0 gives a column that is masked out again)
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                noisy |= (rem[k] != 0u) & ((int32_t)(c0 + (uint32_t)__ffs((int)rem[k]) - 1u) - last[k] > (int32_t)span);
+            if (!__any_sync(kFull, noisy)) {
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (rem[k]) last[k] = (int32_t)(c0 + 31u - (uint32_t)__clz((int)rem[k]));
+                continue;
+            }
+        }
         for (;;) {
             // every lane advances to its next birth inside this word
             uint32_t bj[K], jmin = 32u;
@@ -167,15 +183,38 @@ __device__ __forceinline__ uint32_t walk_row(const Geo& g, uint32_t y, uint32_t 
                     vk[k] = mem[k] ? (uint32_t)tab[k * 32 + lane] : 0u;
                     if (mem[k] && vk[k] == kTentative) vk[k] = resolve_start(g, vexit_chunk, c, y, (uint32_t)(k * 32) + lane);
                 }
+                // rank = how many of the column's newborn have an earlier chain start (starts are distinct: one sample per
+                // cell). Few newborn: one shuffle each. Many (the first column of a dense map gives birth to every value):
+                // their starts go back into the table, 0xFFFF for the others, and every lane counts through it with
+                // 16-byte broadcast loads -- a quarter of the instructions of 64 shuffle rounds.
+                constexpr uint32_t kTableRank = K == 1 ? 4u : K == 2 ? 12u : K == 4 ? 42u : 156u;
+                if (gsz > kTableRank) {
+                    __syncwarp();
 #pragma unroll
-                for (int kk = 0; kk < K; kk++) {
-                    unsigned m2 = mb[kk];
-                    while (m2) {
-                        const int l = __ffs((int)m2) - 1;
-                        const uint32_t v = __shfl_sync(kFull, vk[kk], l);
+                    for (int k = 0; k < K; k++) tab[k * 32 + lane] = mem[k] ? (uint16_t)vk[k] : (uint16_t)0xFFFFu;
+                    __syncwarp();
+                    const uint4* t4 = reinterpret_cast<const uint4*>(tab);
+#pragma unroll 2
+                    for (int q = 0; q < 4 * K; q++) {
+                        const uint4 w4 = t4[q];
+                        const uint32_t h[8] = {w4.x & 0xFFFFu, w4.x >> 16, w4.y & 0xFFFFu, w4.y >> 16,
+                                               w4.z & 0xFFFFu, w4.z >> 16, w4.w & 0xFFFFu, w4.w >> 16};
 #pragma unroll
-                        for (int k = 0; k < K; k++) rank[k] += (v < vk[k]) ? 1u : 0u;
-                        m2 &= m2 - 1u;
+                        for (int e = 0; e < 8; e++)
+#pragma unroll
+                            for (int k = 0; k < K; k++) rank[k] += (h[e] < vk[k]) ? 1u : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < K; kk++) {
+                        unsigned m2 = mb[kk];
+                        while (m2) {
+                            const int l = __ffs((int)m2) - 1;
+                            const uint32_t v = __shfl_sync(kFull, vk[kk], l);
+#pragma unroll
+                            for (int k = 0; k < K; k++) rank[k] += (v < vk[k]) ? 1u : 0u;
+                            m2 &= m2 - 1u;
+                        }
                     }
                 }
                 __syncwarp();
@@ -273,7 +312,7 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
                   unsigned long long* __restrict__ chunktotal, unsigned long long* __restrict__ chunkbase,
                   uint32_t* __restrict__ hso, uint32_t* __restrict__ sync) {
     __shared__ uint2 stage_all[kEventWarps][kEventStage];
-    __shared__ uint16_t tab_all[kEventWarps][32 * K];
+    __shared__ __align__(16) uint16_t tab_all[kEventWarps][32 * K];
     __shared__ __align__(16) uint32_t mstage_all[kEventWarps][2 * event_group(K) * 32 * K];
     __shared__ unsigned long long warp_part[32];
     __shared__ uint32_t last_flag;

@@ -162,6 +162,8 @@ struct shf_buffer {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t aux_stream = nullptr;    // owned: work of a call that is off its critical path (the dictionary of a call
     cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;   // that reads the caller's sample values as compact ids)
+    cudaEvent_t ev_totals = nullptr;
+    bool aux_pending = false;             // the read-backs of the pending call are on aux_stream (ev_aux_join marks their end)
     cudaEvent_t range_ev[8] = {};
     DevBuf din, cmap, vstart, bitmap, prefix, nbiomes, dict, base, colmask, rowtotal, rowbase, chunktotal, chunkbase,
         bins, hso, gstate, evpool, rowinfo, cvt, vexit, sync;
@@ -237,7 +239,9 @@ struct shf_buffer {
         aux_stream = nullptr;
         if (ev_aux_fork) cudaEventDestroy(ev_aux_fork);
         if (ev_aux_join) cudaEventDestroy(ev_aux_join);
-        ev_aux_fork = ev_aux_join = nullptr;
+        if (ev_totals) cudaEventDestroy(ev_totals);
+        ev_aux_fork = ev_aux_join = ev_totals = nullptr;
+        aux_pending = false;
         for (cudaEvent_t& e : range_ev) {
             if (e) cudaEventDestroy(e);
             e = nullptr;
@@ -284,7 +288,7 @@ int launch_events(shf_buffer* b, const Geo& g, cudaStream_t s) {
         shf::events_kernel<K, true><<<egrid, shf::kEventWarps * 32, 0, s>>>(SHF_EVENTS_ARGS);
     } else {
         shf::events_kernel<K, false><<<egrid, shf::kEventWarps * 32, 0, s>>>(SHF_EVENTS_ARGS);
-        shf::bases_kernel<<<g.n_chunks, 256, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
+        shf::bases_kernel<<<(g.n_chunks + 7u) / 8u, 256, 0, s>>>(g, b->rowtotal.as<uint32_t>(), b->rowbase.as<uint32_t>(),
                                                      b->chunktotal.as<unsigned long long>(),
                                                      b->chunkbase.as<unsigned long long>(), b->hso.as<uint32_t>(), counter,
                                                      sync + 2);
@@ -647,6 +651,10 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
     st = dispatch_chain(K, b, g, s, 0);   // (events_kernel leaves the row and chunk bases behind)
     if (st != SHF_OK) return st;
     SHF_CUDA(b->mark(3, s));
+    if (side_dictionary && with_emit) {
+        if (!b->ev_totals) SHF_CUDA(cudaEventCreateWithFlags(&b->ev_totals, cudaEventDisableTiming));
+        SHF_CUDA(cudaEventRecord(b->ev_totals, s));   // the event lists and the totals are done
+    }
     SHF_CUDA(b->mark(4, s));
     if (with_emit) {
         SHF_CUDA(b->mark(5, s));
@@ -656,9 +664,20 @@ int enqueue_speculative(shf_filter* f, shf_buffer* b, const Geo& g, const uint16
         if (st != SHF_OK) return st;
         SHF_CUDA(b->mark(6, s));
     }
-    if (side_dictionary) SHF_CUDA(cudaStreamWaitEvent(s, b->ev_aux_join, 0));
-    SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
-    SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, s));
+    if (side_dictionary && with_emit) {
+        // the numbers settle() looks at travel on the side stream as well: behind the dictionary (already there) and the
+        // event lists, beside the emitting kernel -- nothing of this call is left on the caller's stream after emit, so the
+        // next call's scan starts the moment emit ends
+        SHF_CUDA(cudaStreamWaitEvent(b->aux_stream, b->ev_totals, 0));
+        SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, b->aux_stream));
+        SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, b->aux_stream));
+        SHF_CUDA(cudaEventRecord(b->ev_aux_join, b->aux_stream));
+        b->aux_pending = true;
+    } else {
+        if (side_dictionary) SHF_CUDA(cudaStreamWaitEvent(s, b->ev_aux_join, 0));
+        SHF_CUDA(cudaMemcpyAsync(h_nbiomes, b->nbiomes.p, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, s));
+        SHF_CUDA(cudaMemcpyAsync(h_totals, b->chunktotal.p, ((size_t)n_chunks + 1u) * 8, cudaMemcpyDeviceToHost, s));
+    }
     tls_d2h += (size_t)n_chunks * 16 + 8;
     return SHF_OK;
 }
@@ -709,6 +728,10 @@ int settle(shf_buffer* b) {
     shf_buffer::Deferred d = b->deferred;
     b->deferred.active = false;
     SHF_CUDA(cudaEventSynchronize(b->done_ev));
+    if (b->aux_pending) {
+        SHF_CUDA(cudaEventSynchronize(b->ev_aux_join));
+        b->aux_pending = false;
+    }
     const Geo& g = d.g;
     if (!speculation_holds(b, g, true)) {
         b->last_valid = false;
@@ -748,8 +771,11 @@ int run_on_device(shf_filter* f, shf_buffer* b, const uint16_t* in_dev, uint64_t
     b->has_result = false;
     if (!b->done_ev) SHF_CUDA(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
     if (b->done_recorded && b->done_stream != s) SHF_CUDA(cudaStreamWaitEvent(s, b->done_ev, 0));
-    if ((size_t)n_chunks * 24 + 64 > b->h_small.cap && b->done_recorded)
+    if (b->aux_pending) SHF_CUDA(cudaStreamWaitEvent(s, b->ev_aux_join, 0));   // (read-backs of the call before, long done)
+    if ((size_t)n_chunks * 24 + 64 > b->h_small.cap && b->done_recorded) {
         SHF_CUDA(cudaEventSynchronize(b->done_ev));  // (a copy into the old page-locked block may be in flight)
+        if (b->aux_pending) SHF_CUDA(cudaEventSynchronize(b->ev_aux_join));
+    }
 
     SHF_CUDA(b->bitmap.ensure((size_t)n_chunks * shf::kDictWords * 4));
     SHF_CUDA(b->prefix.ensure((size_t)n_chunks * shf::kDictWords * 4));

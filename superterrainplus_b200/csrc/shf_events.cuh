@@ -354,19 +354,50 @@ __global__ void __launch_bounds__(kEventWarps * 32, K == 1 ? 6 : K == 2 ? 8 : K 
     }
 }
 
-// The same scans for large calls, one CTA per chunk behind events_kernel<K, false>: rows of the chunk, then (the CTA that
-// finishes last) the chunks of the call.
+// The same scans for large calls behind events_kernel<K, false>: one WARP per chunk (a chunk has a few hundred rows: two
+// passes of 32 coalesced loads and a shuffle scan each), eight chunks per CTA; the CTA that finishes last scans the chunk
+// totals of the call.
 __global__ void __launch_bounds__(256) bases_kernel(Geo g, const uint32_t* __restrict__ rowtotal, uint32_t* __restrict__ rowbase,
                                                     unsigned long long* __restrict__ chunktotal,
                                                     unsigned long long* __restrict__ chunkbase, uint32_t* __restrict__ hso,
                                                     unsigned long long* __restrict__ counter, uint32_t* __restrict__ sync) {
     __shared__ unsigned long long warp_part[32];
     __shared__ uint32_t last_flag;
-    const uint32_t n = blockIdx.x;
-    const unsigned long long total = cta_exclusive_scan(rowtotal + (size_t)n * g.H, rowbase + (size_t)n * g.H, g.H, warp_part);
+    const uint32_t lane = threadIdx.x & 31u, n = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (n < g.n_chunks) {
+        const uint32_t* in = rowtotal + (size_t)n * g.H;
+        uint32_t* out = rowbase + (size_t)n * g.H;
+        unsigned long long carry = 0ull;
+        for (uint32_t y0 = 0u; y0 < g.H; y0 += 128u) {   // four rows per lane and round
+            unsigned long long v[4], sum = 0ull;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t y = y0 + lane * 4u + (uint32_t)j;
+                v[j] = y < g.H ? (unsigned long long)in[y] : 0ull;
+                sum += v[j];
+            }
+            unsigned long long incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long u = __shfl_up_sync(kFull, incl, off);
+                if (lane >= (uint32_t)off) incl += u;
+            }
+            unsigned long long at = carry + incl - sum;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t y = y0 + lane * 4u + (uint32_t)j;
+                if (y < g.H) out[y] = (uint32_t)at;   // (garbage if the chunk total overflows 32 bits; the host checks it)
+                at += v[j];
+            }
+            carry += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0u) {
+            chunktotal[n] = carry;
+            hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)carry;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0u) {
-        chunktotal[n] = total;
-        hso[(size_t)n * ((size_t)g.W * g.H + 1u) + (size_t)g.W * g.H] = (uint32_t)total;
         __threadfence();
         last_flag = atomicAdd(&sync[0], 1u) == gridDim.x - 1u;
     }

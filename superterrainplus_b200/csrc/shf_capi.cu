@@ -890,6 +890,7 @@ int run_checked(shf_filter* f, shf_buffer* b, Geo g, const uint16_t* in_dev, boo
         auto plan = [&](uint32_t np, uint32_t extra) {
             g.producers = np;
             g.stages = (np + ppb - 1u) / ppb + extra;
+            g.stages_magic = (uint32_t)((0x100000000ull + g.stages - 1u) / g.stages);
             g.R = g.span + shf::kMarchNB * g.stages;
         };
         auto smem_of = [&](uint32_t t) { return emit_smem(t, g.R, K, (int)g.FW); };

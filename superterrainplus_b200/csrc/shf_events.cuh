@@ -670,7 +670,8 @@ __global__ void __launch_bounds__(K == 1 ? 768 : 640, 1)
         if (t < n_items) fetch(t);
         for (; t < n_items; t += NP) {
             const uint32_t b = t / PPB, pass = t % PPB;
-            const uint32_t gb = gb0 + b, s = gb % stages, cb = b * NB;
+            // (batch -> ring stage and barrier phase without a division: stages is a run-time value; q = gb / stages)
+            const uint32_t gb = gb0 + b, q = __umulhi(gb, g.stages_magic), s = gb - q * stages, cb = b * NB;
             const uint32_t cu = pass * CPP + colq;
             const bool live = cb + cu < PW;
             uint32_t slot = (ring0 + cb) % R + cu;
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(K == 1 ? 768 : 640, 1)
                 wa[0] = a0.x, wa[1] = a0.y, wa[2] = a0.z, wa[3] = a0.w, wa[4] = a1.x, wa[5] = a1.y, wa[6] = a1.z, wa[7] = a1.w;
                 wo[0] = o0.x, wo[1] = o0.y, wo[2] = o0.z, wo[3] = o0.w, wo[4] = o1.x, wo[5] = o1.y, wo[6] = o1.z, wo[7] = o1.w;
             }
-            if (gb >= stages) mbar_wait(&empty_bar[s], (gb / stages - 1u) & 1u, 0x10000000u | (item_k << 16) | gb);  // batch gb - stages is consumed
+            if (gb >= stages) mbar_wait(&empty_bar[s], (q - 1u) & 1u, 0x10000000u | (item_k << 16) | gb);  // batch gb - stages is consumed
             uint8_t* out = cring + (size_t)slot * CS + part * 16u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -762,9 +763,9 @@ __global__ void __launch_bounds__(K == 1 ? 768 : 640, 1)
 
     uint32_t in_slot = ring0, out_slot = (ring0 + R - span % R) % R;
     for (uint32_t b = 0u; b < n_batches; b++) {
-        const uint32_t gb = gb0 + b, s = gb % stages, cb = b * NB;
+        const uint32_t gb = gb0 + b, q = __umulhi(gb, g.stages_magic), s = gb - q * stages, cb = b * NB;
         const uint32_t ce = min(cb + (uint32_t)NB, PW);
-        mbar_wait(&full_bar[s], (gb / stages) & 1u, (item_k << 16) | gb);
+        mbar_wait(&full_bar[s], q & 1u, (item_k << 16) | gb);
         if (row_active) {
             // ---- horizontal window counts of the batch's columns, all values at once (lane = K consecutive ids) ----
             if (cb >= span && ce - cb == (uint32_t)NB && in_slot + NB <= R && out_slot + NB <= R) {

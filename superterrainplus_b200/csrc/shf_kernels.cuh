@@ -54,6 +54,7 @@ struct Geo {
     uint32_t FW;                   // bits per vertical window count: 8 while 2r+1 <= 255, else 16
     uint32_t R;                    // ring columns = span + 16 * stages
     uint32_t stages;               // batches the emit producers may run ahead of the consumers (2..6)
+    uint32_t stages_magic;         // ceil(2^32 / stages): x / stages = umulhi(x, magic) for the batch counts of a launch
     uint32_t producers;            // producer warps of the emit kernel (1..4)
     uint32_t VS;                   // count vector stride in the ring (= Bpad)
     uint32_t cv_pitch, cv_pad;     // column-major (compact id | chain start << 16) map: cvt[(n*PW + c)*cv_pitch + cv_pad + p]

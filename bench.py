@@ -128,58 +128,93 @@ def config_of(wl, n_gpus, scaling):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms; started ahead of the warm-up (nvidia-smi needs a moment
-    to come up), the samples taken inside the timed region are picked by their timestamps."""
+    """SM clock and throttle reasons of one GPU sampled every 20 ms on a thread (NVML through nvidia_ml_py; nvidia-smi
+    polled every 50 ms when NVML cannot be loaded). Started ahead of the warm-up; stop(t0, t1) summarises the samples
+    stamped inside the timed region."""
 
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.rows = []          # (time.time(), sm MHz, max sm MHz, [reasons])
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_of = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                    (getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                    (getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                    (getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(reasons_of(h))
+                        self.rows.append((time.time(), mhz, max_sm, [n for b, n in bits if mask & b]))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._stop.wait(0.02)
+
+            self.source = "nvml, 20 ms"
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            pass
+        self.source = "nvidia-smi -lms 50"
+        q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            cmd = ["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"]
+            if subprocess.run(["which", "stdbuf"], capture_output=True).returncode == 0:
+                cmd = ["stdbuf", "-oL"] + cmd   # (a pipe would otherwise deliver the lines 4 KB at a time)
+            proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.source = None
+            return
+
+        def pump():
+            import datetime
+
+            for ln in proc.stdout:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    self.rows.append((ts, float(f[1]), float(f[2]),
+                                      [n for n, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")]))
+                except (ValueError, IndexError):
+                    continue
+                if self._stop.is_set():
+                    proc.terminate()
+                    break
+
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
 
     def stop(self, t0=None, t1=None):
         """Summary of the samples stamped inside [t0, t1] (time.time() values); all samples when none falls inside."""
-        import datetime
-
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
-            except ValueError:
-                continue
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (nvml and nvidia-smi unavailable)"]}
+        rows = list(self.rows)
         inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
         used = inside or rows
         reasons = sorted({n for r in used for n in r[3]})
         return {"sm_mhz": statistics.median(r[1] for r in used) if used else None,
                 "sm_max_mhz": max(r[2] for r in used) if used else None, "reasons": reasons,
-                "samples": len(used), "samples_in_timed_region": len(inside)}
+                "samples": len(used), "samples_in_timed_region": len(inside), "source": self.source}
 
 
 def measured_traffic(kernel, wl, n_chunks):

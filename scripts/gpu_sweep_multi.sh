@@ -7,8 +7,8 @@ out=gpurun_out/sweep_${tag}.txt
 : > $out
 port=29600
 for dist in uniform blocky; do
-for r in 8 16 32 64 128; do
-for b in 4 16 64 256 1024; do
+for r in ${SWEEP_R:-8 16 32 64 128}; do
+for b in ${SWEEP_B:-4 16 64 256 1024}; do
   chunks=256; if [ "$dist" = uniform ] && [ $b -ge 256 ]; then chunks=64; fi
   port=$((port+1))
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --workload C3 --dist $dist --radius $r --biomes $b --chunks $chunks --steps 5 --warmup 3 --no-cpu --no-e2e --no-consumer --parity-chunks 1 > gpurun_out/sw.json 2> gpurun_out/sw.err

@@ -68,3 +68,8 @@ def test_product_does_not_touch_the_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read()
+    # the measurement scripts run the product and read reports; none of them may execute the checker either
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "scripts", f), errors="replace").read()
+            assert "import oracle" not in text and "from oracle" not in text, f"scripts/{f}"

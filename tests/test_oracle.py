@@ -2,8 +2,11 @@
   1. the reference's own known-answer vector (STPTestHistogram.cpp:44-94),
   2. outputs of the reference's own compiled filter stored in tests/golden/ref_vectors.npz (made by make_golden.py),
   3. the reference build live, when oracle/_ref/libshf_ref.so is present,
-  4. the independent closed-form order rule of SURVEY.md Appendix A.5.
+  4. the independent closed-form order rule of SURVEY.md Appendix A.5,
+  5. digests of the reference build's outputs on the problem sizes of the reference's own benchmark protocol
+     (STPTestHistogram.cpp:215-295: dimension, radius and sample-range sweeps; tests/golden/protocol_digests.json).
 No GPU involved."""
+import json
 import os
 
 import numpy as np
@@ -11,9 +14,11 @@ import pytest
 
 from golden import reference_vector as gv
 from golden.cases import CASES, make_case
+from golden.protocol_cases import NEIGHBOUR, PROTOCOL, digest, make_protocol_map
 from helpers import assert_same
 
 GOLDEN_NPZ = os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz")
+PROTOCOL_DIGESTS = os.path.join(os.path.dirname(__file__), "golden", "protocol_digests.json")
 
 
 def test_reference_known_answer_vector(oracle_mod):
@@ -84,3 +89,22 @@ def test_reference_session_invariants(oracle_mod):
     with pytest.raises(oracle_mod.OracleError) as err:
         oracle_mod.ReferenceSession(0x42)
     assert err.value.status == 2  # STPInvalidEnum
+
+
+@pytest.mark.parametrize("index", range(len(PROTOCOL)))
+def test_port_on_reference_benchmark_protocol(oracle_mod, index):
+    """The shapes the reference benchmarks its filter on (16x16 .. 1024x1024 at radius 16; radius 2 .. 162 at 192x192;
+    sample ranges 2 .. 30): the restatement against the stored digest of the reference build's output, and against the
+    reference build live (both execution types) when it is present."""
+    case = PROTOCOL[index]
+    with open(PROTOCOL_DIGESTS) as f:
+        stored = json.load(f)[index]
+    assert stored["name"] == case["name"]
+    m = make_protocol_map(index)
+    dim = (case["dim"], case["dim"])
+    got = oracle_mod.run_port(m, dim, NEIGHBOUR, case["r"])
+    assert len(got[0]) == stored["bins"] and digest(got) == stored["sha256"], case["name"]
+    if oracle_mod.have_reference():
+        for exec_type in (0x00, 0xFF):
+            assert_same(got, oracle_mod.run_reference(m, dim, NEIGHBOUR, case["r"], exec_type=exec_type),
+                        f"live reference, exec {exec_type:#x}, {case['name']}")

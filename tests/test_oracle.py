@@ -108,3 +108,16 @@ def test_port_on_reference_benchmark_protocol(oracle_mod, index):
         for exec_type in (0x00, 0xFF):
             assert_same(got, oracle_mod.run_reference(m, dim, NEIGHBOUR, case["r"], exec_type=exec_type),
                         f"live reference, exec {exec_type:#x}, {case['name']}")
+
+
+def test_random_differential_restatement_vs_reference_build(oracle_mod):
+    """tests/fuzz_cpu.py: 120 random cases (shapes, radii up to 300, up to 3000 distinct values, five map kinds), the
+    restatement against the reference's own compiled filter, bit for bit."""
+    import subprocess
+    import sys
+
+    if not oracle_mod.have_reference():
+        pytest.skip("reference build not present")
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "fuzz_cpu.py"), "120", "20261017"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "port == reference on" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]

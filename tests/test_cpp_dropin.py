@@ -26,6 +26,17 @@ def test_dropin_compiles_and_fails_loudly_without_gpu(shf):
     assert "cudaGetDeviceCount" in run.stderr or "CUDA" in run.stderr
 
 
+def test_device_free_surface_of_the_cpp_classes(shf):
+    """tests/cpp/test_surface.cpp: copy / move rules, enum values, bin layout, exception hierarchy (static_asserts) and the
+    behaviour of a fresh STPFilterBuffer (type / size echo, null views, moves, STPInvalidEnum); the filter constructor
+    either succeeds (GPU host) or throws STPCUDAError (no CPU path)."""
+    shf.library()
+    build()
+    run = subprocess.run([os.path.join(HERE, "cpp", "test_surface")], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "all C++ surface checks passed" in run.stdout
+
+
 @pytest.mark.gpu
 def test_reference_scenario_in_cpp(shf):
     shf.library()

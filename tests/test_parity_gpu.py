@@ -217,7 +217,7 @@ def test_config5_radius_biome_sweep(shf, filt, oracle_mod, r, biomes, kind):
     (40, 520, 16, 70, "iid", 8), (130, 400, 100, 3, "blocky", 3), (50, 330, 130, 9, "hstripes", 2), (33, 700, 4, 2, "rare", 8),
 ])
 def test_vscan_row_segments(shf, filt, oracle_mod, w, h, r, biomes, kind, segments, monkeypatch):
-    """Small calls split the vertical scan into row segments whose chain starts are resolved afterwards (vpatch_kernel):
+    """Small calls split the vertical scan into row segments whose chain starts are resolved on demand by events_kernel (resolve_start):
     chains that never break (hstripes), chains that break inside segments (rare / small radius), 16-bit ring, and the
     same map with the segmentation switched off must all agree with the oracle."""
     rng = np.random.default_rng(w * 131 + h * 7 + r)

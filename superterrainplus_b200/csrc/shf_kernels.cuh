@@ -16,7 +16,7 @@
 //                           base(c,t)    = per-value counts of the vertical window of the first row of row-tile t
 //   events (shf_events.cuh) : per output row the presence chains of every value along the columns = the life spans of
 //                         the reference accumulator's bins, sorted by birth; their pixel spans total the bins per row
-//   rowscan             : exclusive scan of the bins per row = first-bin index of every row, chunk totals
+//   scans               : bins per row -> first bin of every row and chunk (in events_kernel / bases_kernel; rowscan: wide path)
 //   emit (shf_events.cuh)   : a CTA owns TY consecutive rows (one consumer warp per row); producer warps rebuild the
 //                         vertical window counts of the columns into a shared-memory ring of (2r+1 + 16*stages)
 //                         columns x TY rows x 32K counts; consumers slide them horizontally and write every pixel's

@@ -77,7 +77,7 @@ def parse_args():
     ap.add_argument("--no-consumer", action="store_true")
     ap.add_argument("--sync-steps", action="store_true",
                     help="time the host-blocking shf_run_device instead of back-to-back shf_run_device_async calls")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-sub", type=int, default=32, help="chunks per shf_run_batch call in the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

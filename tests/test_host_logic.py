@@ -85,3 +85,24 @@ def test_two_rank_plumbing_on_gloo(tmp_path):
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "gloo ok" in out.stdout
+
+
+def test_l2_rule_is_decided_from_the_workload_alone():
+    """`config.l2` must say what the GPU arm does and be the same string in both arms: the rule only looks at the
+    workload's definition. The default line (C3 uniform) exceeds the L2 on 1 to 8 GPUs; single sparse chunks do not."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from superterrainplus_b200 import workloads
+
+    c3 = workloads.CONFIGS["C3"]
+    for n_gpus in (1, 2, 4, 8):
+        cfg = bench.config_of(c3, n_gpus, "strong")
+        assert cfg["chunks_per_gpu"] == 256 // n_gpus and cfg["chunks_total"] == 256
+        assert bench.outputs_exceed_l2(c3, cfg["chunks_per_gpu"]) and "exceed" in cfg["l2"]
+        assert bench.config_of(c3, n_gpus, "weak")["chunks_total"] == 256 * n_gpus
+    c1 = workloads.CONFIGS["C1"]
+    assert not bench.outputs_exceed_l2(c1, 1) and "rewritten between steps" in bench.config_of(c1, 1, "strong")["l2"]
+    blocky = dataclasses.replace(workloads.CONFIGS["C2"], dist="blocky")
+    assert not bench.outputs_exceed_l2(blocky, 1)
+    # a lower bound: never claims more than the histograms really hold (uniform C3: 64 bins per pixel)
+    assert 4 + 8 * 32 <= workloads.algorithmic_bytes(dataclasses.replace(c3, chunks=1), 64 * 512 * 512) / (512 * 512)

@@ -300,7 +300,9 @@ def cpu_filter_throughput(wl, host_maps, seconds, all_cores):
             s.close()
     return {"seconds": dt, "value": chunks * w * h / dt / 1e6, "unit": UNIT, "cores": threads_used, "kind": kind,
             "sample": f"{chunks} chunk calls over {len(host_maps)} distinct chunks of the workload in {dt:.1f} s, "
-                      f"{n_workers} filter object(s) x 4 pool threads, host has {cores} logical cores"}
+                      + (f"{n_workers} filter object(s) x 4 pool threads" if kind == "reference" else
+                         f"{n_workers} thread(s) of the single-threaded C restatement")
+                      + f", host has {cores} logical cores"}
 
 
 def run_reference_arm(args):
